@@ -1,0 +1,307 @@
+// d4w_fk.cu -- host side of the f-k filter: plans, mask descriptors, the five launches.
+// C ABI declared in include/d4w.h; replaces dsp.fk_filter_filt / fk_filter_sparsefilt /
+// taper_data and the device side of the mask design functions
+// (/root/reference/src/das4whales/dsp.py:85-171, :308-454, :705-786).
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include "d4w_common.hpp"
+#include "fk_hostplan.hpp"
+#include "fk_kernels.cuh"
+
+using namespace d4w;
+
+namespace d4w {
+std::string& last_error_ref() { static thread_local std::string e; return e; }
+std::atomic<long long>& launch_counter() { static std::atomic<long long> c{0}; return c; }
+}  // namespace d4w
+
+extern "C" const char* d4w_last_error(void) { return last_error_ref().c_str(); }
+extern "C" int d4w_version(void) { return 100; }
+extern "C" long long d4w_launch_count(void) { return launch_counter().load(); }
+
+struct d4w_fk_plan {
+    int nx = 0, ns = 0, device = 0;
+    int t1 = 1, t2 = 0;
+    ColParams col{};
+    RowParams row{};
+    float2 *d_tw_col = nullptr, *d_tw_row = nullptr, *d_twT = nullptr;
+    int *d_k2pos = nullptr, *d_pos2k = nullptr, *d_pos2k_row = nullptr;
+    float* d_taper = nullptr;
+    int col_threads = 256, row_threads = 256;
+    size_t col_smem = 0, row_smem = 0;
+};
+
+struct d4w_fk_mask {
+    d4w_fk_plan* plan = nullptr;
+    MaskParams mp{};
+    double* d_h = nullptr;
+    int nact = 0;
+    std::vector<int> act_k;
+    int *d_act_k = nullptr, *d_k2slot = nullptr;
+    float* d_table = nullptr;      // caller-owned
+};
+
+extern "C" int d4w_fk_plan_create(d4w_fk_plan** out, int nx, int ns, int device) {
+    if (!out) return fail(D4W_ERR_ARG, "d4w_fk_plan_create: null output pointer");
+    *out = nullptr;
+    if (nx < 1 || ns < 1) return fail(D4W_ERR_ARG, "d4w_fk_plan_create: nx and ns must be >= 1");
+    int ndev = 0;
+    D4W_CUDA_TRY(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(D4W_ERR_ARG, "d4w_fk_plan_create: no such CUDA device");
+    DeviceGuard guard(device);
+    cudaDeviceProp prop;
+    D4W_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    const size_t smem_cap = prop.sharedMemPerBlockOptin;
+
+    FkHostPlan hp;
+    std::string err;
+    if (build_fk_hostplan(nx, ns, smem_cap, hp, err)) return fail(D4W_ERR_UNSUPPORTED, err);
+    auto pl = new d4w_fk_plan();
+    pl->nx = nx; pl->ns = ns; pl->device = device;
+    pl->col.pl = hp.colpl; pl->col.nx = nx; pl->col.ns = ns; pl->col.nc = hp.nc; pl->col.nc_shift = hp.nc_shift;
+    pl->col.fstride = hp.fstride; pl->col.aligned = hp.aligned;
+    pl->col_smem = hp.col_smem;
+    pl->col_threads = env_int("D4W_COL_THREADS", 256);
+    pl->t1 = hp.t1; pl->t2 = hp.t2;
+    pl->row.pl = hp.rowpl; pl->row.t1 = hp.t1; pl->row.t2 = hp.t2;
+    pl->row_smem = hp.row_smem;
+    pl->row_threads = env_int("D4W_ROW_THREADS", 256);
+    const auto &twc = hp.tw_col, &twr = hp.tw_row, &twT = hp.twT;
+    const auto &p2k = hp.pos2k, &k2p = hp.k2pos, &p2kr = hp.pos2k_row;
+    const auto& tap = hp.taper;
+    cudaError_t e = cudaSuccess;
+    if (e == cudaSuccess) e = upload(&pl->d_tw_col, twc);
+    if (e == cudaSuccess) e = upload(&pl->d_tw_row, twr);
+    if (e == cudaSuccess) e = upload(&pl->d_twT, twT);
+    if (e == cudaSuccess) e = upload(&pl->d_pos2k, p2k);
+    if (e == cudaSuccess) e = upload(&pl->d_k2pos, k2p);
+    if (e == cudaSuccess) e = upload(&pl->d_pos2k_row, p2kr);
+    if (e == cudaSuccess) e = upload(&pl->d_taper, tap);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_col_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->col_smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_col_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->col_smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_row_mid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->row_smem);
+    if (e != cudaSuccess) {
+        std::string msg = std::string("d4w_fk_plan_create: ") + cudaGetErrorString(e);
+        d4w_fk_plan_destroy(pl);
+        return fail(D4W_ERR_CUDA, msg);
+    }
+    pl->col.tw = pl->d_tw_col; pl->col.k2pos = pl->d_k2pos; pl->col.pos2k = pl->d_pos2k;
+    pl->row.tw = pl->d_tw_row; pl->row.twT = pl->d_twT;
+    *out = pl;
+    return D4W_OK;
+}
+
+extern "C" int d4w_fk_plan_destroy(d4w_fk_plan* pl) {
+    if (!pl) return D4W_OK;
+    DeviceGuard guard(pl->device);
+    cudaFree(pl->d_tw_col); cudaFree(pl->d_tw_row); cudaFree(pl->d_twT);
+    cudaFree(pl->d_k2pos); cudaFree(pl->d_pos2k); cudaFree(pl->d_pos2k_row); cudaFree(pl->d_taper);
+    delete pl;
+    return D4W_OK;
+}
+
+extern "C" int d4w_fk_plan_info(const d4w_fk_plan* pl, int* info) {
+    if (!pl || !info) return fail(D4W_ERR_ARG, "d4w_fk_plan_info: null argument");
+    info[0] = pl->t1; info[1] = pl->t2; info[2] = 2 * pl->col.nc; info[3] = pl->col.pl.nstages;
+    info[4] = pl->row.pl.nstages; info[5] = pl->col_threads; info[6] = pl->row_threads; info[7] = 0;
+    return D4W_OK;
+}
+
+// ------------------------------------------------------------------------------- masks
+static int mask_finish_support(d4w_fk_mask* m, void* stream_v) {
+    d4w_fk_plan* pl = m->plan;
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    const int nrows = pl->nx / 2 + 1;
+    unsigned int* d_rowmax = nullptr;
+    D4W_CUDA_TRY(cudaMalloc((void**)&d_rowmax, nrows * sizeof(unsigned int)));
+    cudaError_t e = cudaMemsetAsync(d_rowmax, 0, nrows * sizeof(unsigned int), stream);
+    if (e == cudaSuccess) {
+        const int fchunk = 8192;
+        dim3 grid((pl->ns + fchunk - 1) / fchunk, nrows);
+        k_mask_rowmax<<<grid, 256, 0, stream>>>(m->mp, d_rowmax, fchunk);
+        e = cudaGetLastError();
+        count_launch();
+    }
+    std::vector<unsigned int> rowmax((size_t)nrows);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(rowmax.data(), d_rowmax, nrows * sizeof(unsigned int), cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    cudaFree(d_rowmax);
+    if (e != cudaSuccess) return fail(D4W_ERR_CUDA, std::string("mask support scan: ") + cudaGetErrorString(e));
+    // exact pruning by default; D4W_MASK_EPS > 0 additionally drops rows whose folded mask never exceeds eps
+    const char* eps_s = std::getenv("D4W_MASK_EPS");
+    const float eps = (eps_s && *eps_s) ? (float)std::atof(eps_s) : 0.0f;
+    std::vector<int> k2slot((size_t)nrows, -1);
+    m->act_k.clear();
+    for (int k = 0; k < nrows; ++k) {
+        float v; std::memcpy(&v, &rowmax[k], 4);
+        if (v > eps) { k2slot[k] = (int)m->act_k.size(); m->act_k.push_back(k); }
+    }
+    m->nact = (int)m->act_k.size();
+    D4W_CUDA_TRY(upload(&m->d_act_k, m->act_k));
+    D4W_CUDA_TRY(upload(&m->d_k2slot, k2slot));
+    return D4W_OK;
+}
+
+static int mask_create_common(d4w_fk_mask** out, d4w_fk_plan* plan, const MaskParams& mp, const double* host_h,
+                              void* stream) {
+    if (!out || !plan) return fail(D4W_ERR_ARG, "mask create: null argument");
+    *out = nullptr;
+    DeviceGuard guard(plan->device);
+    auto m = new d4w_fk_mask();
+    m->plan = plan; m->mp = mp; m->mp.nx = plan->nx; m->mp.ns = plan->ns;
+    if (host_h) {
+        cudaError_t e = cudaMalloc((void**)&m->d_h, (size_t)plan->ns * sizeof(double));
+        if (e == cudaSuccess) e = cudaMemcpy(m->d_h, host_h, (size_t)plan->ns * sizeof(double), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { d4w_fk_mask_destroy(m); return fail(D4W_ERR_CUDA, std::string("mask H upload: ") + cudaGetErrorString(e)); }
+        m->mp.h = m->d_h;
+    }
+    int rc = mask_finish_support(m, stream);
+    if (rc != D4W_OK) { d4w_fk_mask_destroy(m); return rc; }
+    *out = m;
+    return D4W_OK;
+}
+
+extern "C" int d4w_fk_mask_create_fan(d4w_fk_mask** out, d4w_fk_plan* plan, double kval, double fval, double cs_min,
+                                      double cp_min, double cp_max, double cs_max) {
+    MaskParams mp{};
+    mp.kind = MASK_FAN; mp.kval = kval; mp.fval = fval;
+    mp.c0 = cs_min; mp.c1 = cp_min; mp.c2 = cp_max; mp.c3 = cs_max;
+    return mask_create_common(out, plan, mp, nullptr, nullptr);
+}
+
+extern "C" int d4w_fk_mask_create_hybrid_ninf(d4w_fk_mask** out, d4w_fk_plan* plan, double kval, double fval,
+                                              double cs_min, double cp_min, double cp_max, double cs_max,
+                                              const double* host_H, int col_lo, int col_hi) {
+    if (!host_H) return fail(D4W_ERR_ARG, "hybrid mask: null H profile");
+    MaskParams mp{};
+    mp.kind = MASK_HYBRID_NINF; mp.kval = kval; mp.fval = fval;
+    mp.c0 = cs_min; mp.c1 = cp_min; mp.c2 = cp_max; mp.c3 = cs_max;
+    mp.col_lo = col_lo; mp.col_hi = col_hi;
+    return mask_create_common(out, plan, mp, host_H, nullptr);
+}
+
+extern "C" int d4w_fk_mask_create_dense(d4w_fk_mask** out, d4w_fk_plan* plan, const float* dev_mask, void* stream) {
+    if (!dev_mask) return fail(D4W_ERR_ARG, "dense mask: null device pointer");
+    MaskParams mp{};
+    mp.kind = MASK_DENSE; mp.dense = dev_mask;
+    return mask_create_common(out, plan, mp, nullptr, stream);
+}
+
+extern "C" int d4w_fk_mask_destroy(d4w_fk_mask* m) {
+    if (!m) return D4W_OK;
+    DeviceGuard guard(m->plan->device);
+    cudaFree(m->d_h); cudaFree(m->d_act_k); cudaFree(m->d_k2slot);
+    delete m;
+    return D4W_OK;
+}
+
+extern "C" int d4w_fk_mask_rows(const d4w_fk_mask* m) { return m ? m->nact : 0; }
+
+extern "C" size_t d4w_fk_mask_table_bytes(const d4w_fk_mask* m) {
+    if (!m) return 0;
+    return std::max<size_t>((size_t)m->nact * m->plan->ns * sizeof(float), 16);
+}
+
+extern "C" int d4w_fk_mask_build(d4w_fk_mask* m, float* dev_table, void* stream_v) {
+    if (!m || !dev_table) return fail(D4W_ERR_ARG, "d4w_fk_mask_build: null argument");
+    d4w_fk_plan* pl = m->plan;
+    DeviceGuard guard(pl->device);
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    m->d_table = dev_table;
+    const size_t total = (size_t)m->nact * pl->ns;
+    if (total == 0) return D4W_OK;
+    const double scale = 1.0 / ((double)pl->nx * (double)pl->ns);
+    const size_t blocks = (total + 255) / 256;
+    if (blocks > 0x7fffffffull) return fail(D4W_ERR_UNSUPPORTED, "mask table too large for one launch");
+    k_mask_build<<<(unsigned)blocks, 256, 0, stream>>>(m->mp, dev_table, m->d_act_k, pl->d_pos2k_row, pl->t1, pl->t2,
+                                                      scale, total);
+    D4W_CHECK_LAUNCH("k_mask_build");
+    return D4W_OK;
+}
+
+extern "C" int d4w_fk_mask_materialize(const d4w_fk_mask* m, double* dev_out, void* stream_v) {
+    if (!m || !dev_out) return fail(D4W_ERR_ARG, "d4w_fk_mask_materialize: null argument");
+    DeviceGuard guard(m->plan->device);
+    const size_t total = (size_t)m->plan->nx * m->plan->ns;
+    const size_t blocks = (total + 255) / 256;
+    if (blocks > 0x7fffffffull) return fail(D4W_ERR_UNSUPPORTED, "mask too large for one launch");
+    k_mask_materialize<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_v>>>(m->mp, dev_out, total);
+    D4W_CHECK_LAUNCH("k_mask_materialize");
+    return D4W_OK;
+}
+
+// ------------------------------------------------------------------------------- apply
+extern "C" size_t d4w_fk_workspace_bytes(const d4w_fk_plan* pl, const d4w_fk_mask* m) {
+    if (!pl || !m) return 0;
+    return std::max<size_t>((size_t)m->nact * pl->ns * sizeof(float2), 16);
+}
+
+template <bool INV>
+static int launch_row_split(const d4w_fk_plan* pl, float2* w, int nact, cudaStream_t stream) {
+    const int threads = 128;
+    dim3 grid((pl->t2 + threads - 1) / threads, nact);
+    const size_t ldw = (size_t)pl->ns;
+    switch (pl->t1) {
+#define D4W_T1CASE(T) case T: k_row_split<T, INV><<<grid, threads, 0, stream>>>(w, ldw, pl->t2, pl->d_twT); break;
+        D4W_T1CASE(2) D4W_T1CASE(3) D4W_T1CASE(4) D4W_T1CASE(5) D4W_T1CASE(6) D4W_T1CASE(8) D4W_T1CASE(10)
+        D4W_T1CASE(12) D4W_T1CASE(15) D4W_T1CASE(16) D4W_T1CASE(20) D4W_T1CASE(25)
+#undef D4W_T1CASE
+        default: return fail(D4W_ERR_UNSUPPORTED, "row split radix not built");
+    }
+    D4W_CHECK_LAUNCH("k_row_split");
+    return D4W_OK;
+}
+
+extern "C" int d4w_fk_apply_pass(d4w_fk_plan* pl, d4w_fk_mask* m, const float* x, float* y, void* ws, int taper,
+                                 int pass, void* stream_v) {
+    if (!pl || !m || !ws) return fail(D4W_ERR_ARG, "d4w_fk_apply: null argument");
+    if (m->plan != pl) return fail(D4W_ERR_ARG, "d4w_fk_apply: mask was built for a different plan");
+    if (!m->d_table) return fail(D4W_ERR_ARG, "d4w_fk_apply: call d4w_fk_mask_build first");
+    DeviceGuard guard(pl->device);
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    float2* w = (float2*)ws;
+    const size_t ldw = (size_t)pl->ns;
+    const int tile = 2 * pl->col.nc;
+    const int ntiles = (pl->ns + tile - 1) / tile;
+    const int nact = m->nact;
+    switch (pass) {
+        case 1:
+            if (!x) return fail(D4W_ERR_ARG, "d4w_fk_apply: null input");
+            if (nact == 0) return D4W_OK;
+            k_col_fwd<<<ntiles, pl->col_threads, pl->col_smem, stream>>>(pl->col, x, w, ldw, m->d_act_k, nact,
+                                                                         taper ? pl->d_taper : nullptr);
+            D4W_CHECK_LAUNCH("k_col_fwd");
+            return D4W_OK;
+        case 2:
+            if (pl->t1 == 1 || nact == 0) return D4W_OK;
+            return launch_row_split<false>(pl, w, nact, stream);
+        case 3: {
+            if (nact == 0) return D4W_OK;
+            dim3 grid(pl->t1, nact);
+            k_row_mid<<<grid, pl->row_threads, pl->row_smem, stream>>>(pl->row, w, ldw, m->d_table, (size_t)pl->ns);
+            D4W_CHECK_LAUNCH("k_row_mid");
+            return D4W_OK;
+        }
+        case 4:
+            if (pl->t1 == 1 || nact == 0) return D4W_OK;
+            return launch_row_split<true>(pl, w, nact, stream);
+        case 5:
+            if (!y) return fail(D4W_ERR_ARG, "d4w_fk_apply: null output");
+            k_col_inv<<<ntiles, pl->col_threads, pl->col_smem, stream>>>(pl->col, w, ldw, m->d_k2slot, y);
+            D4W_CHECK_LAUNCH("k_col_inv");
+            return D4W_OK;
+        default:
+            return fail(D4W_ERR_ARG, "d4w_fk_apply_pass: pass must be 1..5");
+    }
+}
+
+extern "C" int d4w_fk_apply(d4w_fk_plan* pl, d4w_fk_mask* m, const float* x, float* y, void* ws, int taper,
+                            void* stream) {
+    for (int pass = 1; pass <= 5; ++pass) {
+        int rc = d4w_fk_apply_pass(pl, m, x, y, ws, taper, pass, stream);
+        if (rc != D4W_OK) return rc;
+    }
+    return D4W_OK;
+}

@@ -1,0 +1,106 @@
+// fk_hostplan.hpp -- host-only planning of the f-k filter (tile width, T1 x T2 split of the
+// time axis, twiddle / digit-reversal / taper tables).  Shared by d4w_fk.cu (which uploads
+// the tables) and tests/host_emul (which runs the kernel bodies on the CPU).
+#pragma once
+#include <cstdlib>
+#include "fft_plan.hpp"
+
+namespace d4w {
+
+struct FkHostPlan {
+    int nx = 0, ns = 0;
+    int t1 = 1, t2 = 0, nc = 1, nc_shift = 0, fstride = 0, aligned = 0;
+    FftPlan colpl{}, rowpl{};
+    std::vector<float2> tw_col, tw_row, twT;
+    std::vector<int> pos2k, k2pos, pos2k_row;
+    std::vector<float> taper;
+    size_t col_smem = 0, row_smem = 0;
+};
+
+inline int env_int(const char* name, int dflt) {
+    const char* s = std::getenv(name);
+    return (s && *s) ? std::atoi(s) : dflt;
+}
+
+// scipy.signal.windows.tukey(M, alpha) (sym=True): the window dsp.taper_data applies (dsp.py:721)
+inline std::vector<float> tukey_window(int m, double alpha) {
+    std::vector<float> w((size_t)std::max(m, 0), 1.0f);
+    if (m <= 1 || alpha <= 0) return w;
+    const double pi = 3.14159265358979323846;
+    if (alpha >= 1.0) {
+        for (int n = 0; n < m; ++n) w[n] = (float)(0.5 - 0.5 * std::cos(2.0 * pi * n / (m - 1)));
+        return w;
+    }
+    const int width = (int)std::floor(alpha * (m - 1) / 2.0);
+    for (int n = 0; n <= width; ++n)
+        w[n] = (float)(0.5 * (1.0 + std::cos(pi * (-1.0 + 2.0 * n / alpha / (m - 1)))));
+    for (int n = m - width - 1; n < m; ++n)
+        w[n] = (float)(0.5 * (1.0 + std::cos(pi * (-2.0 / alpha + 1.0 + 2.0 * n / alpha / (m - 1)))));
+    return w;
+}
+
+inline const std::vector<int>& split_radices() {
+    static const std::vector<int> r = {1, 2, 3, 4, 5, 6, 8, 10, 12, 15, 16, 20, 25};
+    return r;
+}
+
+// returns 0 on success; 1 = unsupported shape (err says why)
+inline int build_fk_hostplan(int nx, int ns, size_t smem_cap, FkHostPlan& hp, std::string& err) {
+    hp.nx = nx; hp.ns = ns;
+    const int col_maxr = env_int("D4W_COL_MAX_RADIX", 25);
+    const int row_maxr = env_int("D4W_ROW_MAX_RADIX", 16);
+    std::string e2;
+    if (!make_plan(nx, col_maxr, hp.colpl, e2)) { err = "channel axis: " + e2; return 1; }
+    int nc = 8;
+    const size_t col_budget = std::min<size_t>(smem_cap, 200 * 1024);
+    while (nc > 1 && (size_t)nc * (nx + 1) * sizeof(float2) > col_budget) nc >>= 1;
+    if ((size_t)nc * (nx + 1) * sizeof(float2) > smem_cap) {
+        err = "channel axis too long for one SM's shared memory (" + std::to_string(nx) + " channels); shard the matrix over GPUs";
+        return 1;
+    }
+    const int forced_nc = env_int("D4W_COL_NC", 0);
+    if ((forced_nc == 1 || forced_nc == 2 || forced_nc == 4 || forced_nc == 8) &&
+        (size_t)forced_nc * (nx + 1) * sizeof(float2) <= smem_cap) nc = forced_nc;
+    hp.nc = nc;
+    hp.nc_shift = (nc == 1) ? 0 : (nc == 2) ? 1 : (nc == 4) ? 2 : 3;
+    hp.fstride = nx | 1;
+    hp.aligned = (ns % 2 == 0) ? 1 : 0;
+    hp.col_smem = (size_t)nc * hp.fstride * sizeof(float2);
+
+    int t1 = 0;
+    const int forced_t1 = env_int("D4W_T1", 0);
+    for (int cand : split_radices()) {
+        if (forced_t1 > 0 && cand != forced_t1) continue;
+        if (ns % cand) continue;
+        const int t2 = ns / cand;
+        const int limit = (cand == 1) ? 16384 : 10240;
+        if (forced_t1 == 0 && t2 > limit) continue;
+        if ((size_t)t2 * sizeof(float2) > smem_cap) continue;
+        FftPlan tmp;
+        if (!make_plan(t2, row_maxr, tmp, e2)) continue;
+        t1 = cand; hp.rowpl = tmp;
+        break;
+    }
+    if (t1 == 0) {
+        err = "time axis length " + std::to_string(ns) +
+              " has no supported split (needs ns = T1*T2 with T1 <= 25, T2 <= 10240 and prime factors <= 61)";
+        return 1;
+    }
+    hp.t1 = t1; hp.t2 = ns / t1;
+    hp.row_smem = (size_t)hp.t2 * sizeof(float2);
+    hp.tw_col = make_twiddles(nx);
+    hp.tw_row = make_twiddles(hp.t2);
+    hp.twT.resize((size_t)hp.t2);
+    for (int j = 0; j < hp.t2; ++j) {
+        const double a = 6.283185307179586476925286766559 * (double)j / (double)ns;
+        hp.twT[j] = make_float2((float)std::cos(a), (float)(-std::sin(a)));
+    }
+    hp.pos2k = make_pos2freq(hp.colpl);
+    hp.k2pos.assign((size_t)nx, 0);
+    for (int p = 0; p < nx; ++p) hp.k2pos[hp.pos2k[p]] = p;
+    hp.pos2k_row = make_pos2freq(hp.rowpl);
+    hp.taper = tukey_window(ns, 0.03);
+    return 0;
+}
+
+}  // namespace d4w

@@ -1,0 +1,291 @@
+// fk_kernels.cuh -- the five passes of the support-pruned f-k filter and the mask builders.
+//
+//   x[c][t] real  --P1-->  W[slot][t]   (R2C along channels, 2*NC time samples per tile, only
+//                                        wavenumber rows whose folded mask is non-zero are kept)
+//   W  --P2-->  W      radix-T1 split of the length-ns time transform (streaming, registers only)
+//   W  --P3-->  W      length-T2 FFT -> x folded mask -> length-T2 inverse FFT (one smem visit)
+//   W  --P4-->  W      inverse radix-T1 split
+//   W  --P5-->  y[c][t] real  (C2R along channels)
+//
+// Reference arithmetic replaced: dsp.fk_filter_filt / fk_filter_sparsefilt
+// (/root/reference/src/das4whales/dsp.py:725-786) and the mask definitions of
+// dsp.fk_filter_design (:85-171) and dsp.hybrid_ninf_filter_design (:308-454).
+//
+// Each kernel body is a __host__ __device__ function of (block index, tid, nthr, smem) whose
+// per-thread loops are `for (i = tid; i < n; i += nthr)`, so tests/host_emul runs the very
+// same code on the CPU with nthr = 1.
+#pragma once
+#include "fft_smem.cuh"
+
+namespace d4w {
+
+struct ColParams {
+    FftPlan pl;
+    const float2* tw;      // W_nx^j
+    const int* k2pos;      // frequency index -> smem position after the forward stages
+    const int* pos2k;      // inverse map
+    int nx, ns;
+    int nc;                // complex columns per tile (tile = 2*nc time samples)
+    int nc_shift;          // log2(nc)
+    int fstride;           // smem stride between columns (float2 units)
+    int aligned;           // rows 8-byte aligned (ns even) -> float2 global accesses
+};
+
+struct RowParams {
+    FftPlan pl;            // length T2
+    const float2* tw;      // W_T2^j
+    const float2* twT;     // W_ns^j for j < T2 (split twiddles)
+    int t1, t2;
+};
+
+enum { MASK_FAN = 0, MASK_HYBRID_NINF = 1, MASK_DENSE = 2 };
+
+struct MaskParams {
+    int kind;
+    int nx, ns;
+    double kval, fval;               // numpy fftfreq steps
+    double c0, c1, c2, c3;           // cs_min, cp_min, cp_max, cs_max
+    const double* h;                 // hybrid: H(f) profile over the shifted axis (ns entries)
+    int col_lo, col_hi;              // hybrid: speed-filtered column range
+    const float* dense;              // dense: [nx][ns] shifted layout
+};
+
+// ------------------------------------------------------------------ mask definitions
+// Value of the reference's mask at shifted-layout index (i, j), in double.
+__host__ __device__ inline double mask_fan(const MaskParams& mp, int i, int j) {
+    const double k = (double)(i - mp.nx / 2) * mp.kval;       // dsp.py:130
+    if (fabs(k) < 0.005) return 0.0;                          // dsp.py:142
+    const double f = (double)(j - mp.ns / 2) * mp.fval;       // dsp.py:129
+    const double v = fabs(f / k);                             // dsp.py:146
+    const double half_pi = 1.57079632679489661923;
+    double m = 1.0;
+    if (v >= mp.c0 && v <= mp.c1) m = sin(half_pi * (v - mp.c0) / (mp.c1 - mp.c0));          // :149-151
+    if (v >= mp.c2 && v <= mp.c3) m = 1.0 - sin(half_pi * (v - mp.c2) / (mp.c3 - mp.c2));    // :153-155
+    if (v >= mp.c3) m = 0.0;                                  // :157
+    if (v < mp.c0) m = 0.0;                                   // :158
+    return m;
+}
+
+__host__ __device__ inline double hybrid_a(const MaskParams& mp, int i, int j) {
+    double a = mp.h[j];                                       // dsp.py:372 (tiled H)
+    if (j >= mp.col_lo && j < mp.col_hi) {                    // dsp.py:376
+        const double half_pi = 1.57079632679489661923;
+        const double f = (double)(j - mp.ns / 2) * mp.fval;
+        const double k = (double)(i - mp.nx / 2) * mp.kval;
+        const double ks_lo = f / mp.c3, kp_lo = f / mp.c2;    // :381-382
+        const double ks_hi = f / mp.c0, kp_hi = f / mp.c1;    // :384-385
+        double col = 0.0;
+        if (ks_lo != kp_lo && k >= ks_lo && k <= kp_lo) col = sin(half_pi * (k - ks_lo) / (kp_lo - ks_lo));   // :388-391
+        if (ks_hi != kp_hi && k >= kp_hi && k <= ks_hi) col = -sin(half_pi * (k - ks_hi) / (ks_hi - kp_hi));  // :392-395
+        if (k > kp_lo && k < kp_hi) col = 1.0;                // :399
+        a *= col;                                             // :402
+    }
+    return a;
+}
+
+__host__ __device__ inline double mask_shifted(const MaskParams& mp, int i, int j) {
+    switch (mp.kind) {
+        case MASK_FAN: return mask_fan(mp, i, j);
+        case MASK_HYBRID_NINF: {                              // += fliplr ; += flipud  (dsp.py:405-406)
+            const int i2 = mp.nx - 1 - i, j2 = mp.ns - 1 - j;
+            return hybrid_a(mp, i, j) + hybrid_a(mp, i, j2) + hybrid_a(mp, i2, j) + hybrid_a(mp, i2, j2);
+        }
+        default: return (double)mp.dense[(size_t)i * mp.ns + j];
+    }
+}
+
+// Folded mask at un-shifted DFT indices (k, f):  (M[k,f] + M[-k,-f]) / 2   
+__host__ __device__ inline double mask_folded(const MaskParams& mp, int k, int f) {
+    const int nx = mp.nx, ns = mp.ns;
+    const int i1 = (k + nx / 2) % nx, j1 = (f + ns / 2) % ns;
+    const int i2 = ((nx - k) % nx + nx / 2) % nx, j2 = ((ns - f) % ns + ns / 2) % ns;
+    return 0.5 * (mask_shifted(mp, i1, j1) + mask_shifted(mp, i2, j2));
+}
+
+// row-support scan: rowmax[k] = max_f |M_sym[k][f]| for k in [0, nx/2]  (float bits, atomicMax)
+__host__ __device__ inline void body_mask_rowmax(const MaskParams& mp, unsigned int* rowmax, int k, int fchunk0,
+                                                 int fchunk1, int tid, int nthr) {
+    float m = 0.f;
+    for (int f = fchunk0 + tid; f < fchunk1; f += nthr) m = fmaxf(m, (float)fabs(mask_folded(mp, k, f)));
+#ifdef __CUDA_ARCH__
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((tid & 31) == 0 && m > 0.f) atomicMax(rowmax + k, __float_as_uint(m));
+#else
+    unsigned int u; memcpy(&u, &m, 4);
+    if (u > rowmax[k]) rowmax[k] = u;
+#endif
+}
+
+// transform-order table: tab[slot][kt1][p] = M_sym[act_k[slot]][kt1 + T1*pos2k_row[p]] * scale
+__host__ __device__ inline void body_mask_build(const MaskParams& mp, float* tab, const int* act_k, const int* pos2k_row,
+                                                int t1, int t2, double scale, size_t idx) {
+    const int p = (int)(idx % t2);
+    const size_t r = idx / t2;
+    const int kt1 = (int)(r % t1);
+    const int slot = (int)(r / t1);
+    const int f = kt1 + t1 * pos2k_row[p];
+    tab[idx] = (float)(mask_folded(mp, act_k[slot], f) * scale);
+}
+
+// ------------------------------------------------------------------ P1: column forward (R2C over channels)
+__host__ __device__ inline void body_col_fwd(const ColParams& cp, const float* __restrict__ x, float2* __restrict__ w,
+                                             size_t ldw, const int* __restrict__ act_k, int nact,
+                                             const float* __restrict__ taper, int bx, int tid, int nthr, float2* smem) {
+    const int nc = cp.nc, sh = cp.nc_shift, ns = cp.ns, nx = cp.nx;
+    const int t0 = bx * 2 * nc;
+    for (int i = tid; i < (nx << sh); i += nthr) {
+        const int c = i >> sh, col = i & (nc - 1);
+        const int t = t0 + 2 * col;
+        const float* row = x + (size_t)c * ns;
+        float a = 0.f, b = 0.f;
+        if (t + 1 < ns) {
+            if (cp.aligned) { const float2 v = *reinterpret_cast<const float2*>(row + t); a = v.x; b = v.y; }
+            else { a = row[t]; b = row[t + 1]; }
+            if (taper) { a *= taper[t]; b *= taper[t + 1]; }
+        } else if (t < ns) {
+            a = row[t];
+            if (taper) a *= taper[t];
+        }
+        smem[col * cp.fstride + c] = make_float2(a, b);
+    }
+    D4W_SYNC();
+    fft_forward_stages(smem, cp.pl, cp.tw, nc, cp.fstride, tid, nthr, 0, cp.pl.nstages);
+    // two-for-one untangle: column z = x_t + i*x_{t+1}  ->  X_t[k], X_{t+1}[k] for the kept rows
+    for (int i = tid; i < (nact << sh); i += nthr) {
+        const int slot = i >> sh, col = i & (nc - 1);
+        const int k = act_k[slot];
+        const int p = cp.k2pos[k], p2 = cp.k2pos[k == 0 ? 0 : nx - k];
+        const float2 z = smem[col * cp.fstride + p], z2 = smem[col * cp.fstride + p2];
+        const float2 xa = make_float2(0.5f * (z.x + z2.x), 0.5f * (z.y - z2.y));   // (z + conj z2)/2
+        const float2 xb = make_float2(0.5f * (z.y + z2.y), 0.5f * (z2.x - z.x));   // (z - conj z2)/(2i)
+        const int t = t0 + 2 * col;
+        float2* o = w + (size_t)slot * ldw + t;
+        if (t < ns) o[0] = xa;
+        if (t + 1 < ns) o[1] = xb;
+    }
+}
+
+// ------------------------------------------------------------------ P5: column inverse (C2R over channels)
+__host__ __device__ inline void body_col_inv(const ColParams& cp, const float2* __restrict__ w, size_t ldw,
+                                             const int* __restrict__ k2slot, float* __restrict__ y, int bx, int tid,
+                                             int nthr, float2* smem) {
+    const int nc = cp.nc, sh = cp.nc_shift, ns = cp.ns, nx = cp.nx;
+    const int t0 = bx * 2 * nc;
+    for (int i = tid; i < (nx << sh); i += nthr) {
+        const int p = i >> sh, col = i & (nc - 1);
+        const int k = cp.pos2k[p];
+        const int kk = (2 * k <= nx) ? k : nx - k;
+        const int slot = k2slot[kk];
+        float2 z = make_float2(0.f, 0.f);
+        if (slot >= 0) {
+            const int t = t0 + 2 * col;
+            const float2* src = w + (size_t)slot * ldw + t;
+            float2 y0 = make_float2(0.f, 0.f), y1 = make_float2(0.f, 0.f);
+            if (t < ns) y0 = src[0];
+            if (t + 1 < ns) y1 = src[1];
+            if (kk == 0 || 2 * kk == nx) { y0.y = 0.f; y1.y = 0.f; }      // self-conjugate rows are real
+            if (k == kk) z = make_float2(y0.x - y1.y, y0.y + y1.x);       // Y_t + i Y_{t+1}
+            else         z = make_float2(y0.x + y1.y, y1.x - y0.y);       // conj(Y_t) + i conj(Y_{t+1})
+        }
+        smem[col * cp.fstride + p] = z;
+    }
+    D4W_SYNC();
+    fft_inverse_stages(smem, cp.pl, cp.tw, nc, cp.fstride, tid, nthr, 0, cp.pl.nstages);
+    for (int i = tid; i < (nx << sh); i += nthr) {
+        const int c = i >> sh, col = i & (nc - 1);
+        const float2 z = smem[col * cp.fstride + c];
+        const int t = t0 + 2 * col;
+        float* row = y + (size_t)c * ns;
+        if (t + 1 < ns) {
+            if (cp.aligned) *reinterpret_cast<float2*>(row + t) = z;
+            else { row[t] = z.x; row[t + 1] = z.y; }
+        } else if (t < ns) {
+            row[t] = z.x;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ P2 / P4: radix-T1 time split (registers only)
+template <int T1, bool INV>
+__host__ __device__ inline void body_row_split(float2* __restrict__ w, size_t ldw, int t2len, const float2* __restrict__ twT,
+                                               int slot, int t2) {
+    float2* base = w + (size_t)slot * ldw + t2;
+    float2 v[T1];
+    static_for<T1>([&](auto jc) { constexpr int j = decltype(jc)::value; v[j] = base[(size_t)j * t2len]; });
+    float2 p[T1];
+    twiddle_powers<T1>(twT[t2], p);
+    if constexpr (!INV) {
+        DFT<T1, false>::run(v);
+        static_for<T1>([&](auto jc) { constexpr int j = decltype(jc)::value; if constexpr (j > 0) v[j] = cmul(v[j], p[j]); });
+    } else {
+        static_for<T1>([&](auto jc) { constexpr int j = decltype(jc)::value; if constexpr (j > 0) v[j] = cmulc(v[j], p[j]); });
+        DFT<T1, true>::run(v);
+    }
+    static_for<T1>([&](auto jc) { constexpr int j = decltype(jc)::value; base[(size_t)j * t2len] = v[j]; });
+}
+
+// ------------------------------------------------------------------ P3: FFT(T2) -> x table -> IFFT(T2)
+// `tab` is indexed [slot*tab_slot_stride + kt1*T2 + p] in transform (digit-reversed) order;
+// tab_slot_stride = 0 shares one table between all rows (Hilbert weights, template spectra).
+__host__ __device__ inline void body_row_mid(const RowParams& rp, float2* __restrict__ w, size_t ldw,
+                                             const float* __restrict__ tab, size_t tab_slot_stride, int kt1, int slot,
+                                             int tid, int nthr, float2* smem) {
+    const int n = rp.t2;
+    float2* g = w + (size_t)slot * ldw + (size_t)kt1 * n;
+    for (int i = tid; i < n; i += nthr) smem[i] = g[i];
+    D4W_SYNC();
+    fft_forward_stages(smem, rp.pl, rp.tw, 1, n, tid, nthr, 0, rp.pl.nstages);
+    const float* m = tab + (size_t)slot * tab_slot_stride + (size_t)kt1 * n;
+    for (int i = tid; i < n; i += nthr) { const float s = m[i]; float2 v = smem[i]; v.x *= s; v.y *= s; smem[i] = v; }
+    D4W_SYNC();
+    fft_inverse_stages(smem, rp.pl, rp.tw, 1, n, tid, nthr, 0, rp.pl.nstages);
+    for (int i = tid; i < n; i += nthr) g[i] = smem[i];
+}
+
+// ================================================================== __global__ wrappers
+#ifdef __CUDACC__
+extern __shared__ float2 d4w_dyn_smem[];
+
+__global__ void __launch_bounds__(256, 1)
+k_col_fwd(ColParams cp, const float* __restrict__ x, float2* __restrict__ w, size_t ldw, const int* __restrict__ act_k,
+          int nact, const float* __restrict__ taper) {
+    body_col_fwd(cp, x, w, ldw, act_k, nact, taper, blockIdx.x, threadIdx.x, blockDim.x, d4w_dyn_smem);
+}
+
+__global__ void __launch_bounds__(256, 1)
+k_col_inv(ColParams cp, const float2* __restrict__ w, size_t ldw, const int* __restrict__ k2slot, float* __restrict__ y) {
+    body_col_inv(cp, w, ldw, k2slot, y, blockIdx.x, threadIdx.x, blockDim.x, d4w_dyn_smem);
+}
+
+template <int T1, bool INV>
+__global__ void __launch_bounds__(128)
+k_row_split(float2* __restrict__ w, size_t ldw, int t2len, const float2* __restrict__ twT) {
+    const int t2 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t2 < t2len) body_row_split<T1, INV>(w, ldw, t2len, twT, blockIdx.y, t2);
+}
+
+__global__ void __launch_bounds__(256, 2)
+k_row_mid(RowParams rp, float2* __restrict__ w, size_t ldw, const float* __restrict__ tab, size_t tab_slot_stride) {
+    body_row_mid(rp, w, ldw, tab, tab_slot_stride, blockIdx.x, blockIdx.y, threadIdx.x, blockDim.x, d4w_dyn_smem);
+}
+
+__global__ void k_mask_rowmax(MaskParams mp, unsigned int* rowmax, int fchunk) {
+    const int k = blockIdx.y;
+    const int f0 = blockIdx.x * fchunk;
+    const int f1 = min(mp.ns, f0 + fchunk);
+    body_mask_rowmax(mp, rowmax, k, f0, f1, threadIdx.x, blockDim.x);
+}
+
+__global__ void k_mask_build(MaskParams mp, float* tab, const int* act_k, const int* pos2k_row, int t1, int t2,
+                             double scale, size_t total) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < total) body_mask_build(mp, tab, act_k, pos2k_row, t1, t2, scale, idx);
+}
+
+__global__ void k_mask_materialize(MaskParams mp, double* out, size_t total) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < total) out[idx] = mask_shifted(mp, (int)(idx / mp.ns), (int)(idx % mp.ns));
+}
+#endif  // __CUDACC__
+
+}  // namespace d4w

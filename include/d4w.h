@@ -1,0 +1,97 @@
+/* d4w.h -- C ABI of libd4w.so, the B200-native (sm_100a) replacement for the channel-parallel
+ * DSP hot path of DAS4Whales.
+ *
+ * The reference has no FFI: its boundary is the Python module namespace
+ * (`das4whales.dsp.*`, `das4whales.detect.*`).  Each entry point below names the reference
+ * function(s) whose arithmetic it replaces (file:line under /root/reference/src/das4whales/).
+ * das4whales_b200/{dsp,detect}.py keep the reference signatures and call these through cffi
+ * (ABI mode; the block between D4W_CDEF_BEGIN / D4W_CDEF_END is fed to ffi.cdef verbatim).
+ *
+ * Conventions: plain pointers and sizes only; every `dev_` pointer is CUDA device memory on
+ * the plan's device; `stream` is a cudaStream_t passed as void* (NULL = legacy default
+ * stream); all calls are asynchronous on `stream` unless stated; the return value is a
+ * d4w_status (0 = ok) and d4w_last_error() gives the message for the calling thread.
+ * There is no CPU fallback anywhere behind this interface.
+ */
+#ifndef D4W_H
+#define D4W_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* D4W_CDEF_BEGIN */
+typedef struct d4w_fk_plan d4w_fk_plan;
+typedef struct d4w_fk_mask d4w_fk_mask;
+
+enum {
+    D4W_OK = 0,
+    D4W_ERR_ARG = 1,          /* bad shape / null pointer / inconsistent arguments        */
+    D4W_ERR_UNSUPPORTED = 2,  /* FFT length with a prime factor > 61, matrix too large ... */
+    D4W_ERR_CUDA = 3,         /* a CUDA runtime call failed (message has the cudaError)    */
+    D4W_ERR_NCCL = 4
+};
+
+const char* d4w_last_error(void);
+int d4w_version(void);
+/* number of kernels launched by this library since load (bench.py's gpu_launches) */
+long long d4w_launch_count(void);
+
+/* ---- f-k filter: dsp.fk_filter_filt (dsp.py:725-756), dsp.fk_filter_sparsefilt (:759-786),
+ *      dsp.taper_data (:705-722) ------------------------------------------------------- */
+/* Plan for an [nx channels] x [ns samples] float32 strain matrix on CUDA device `device`. */
+int d4w_fk_plan_create(d4w_fk_plan** out, int nx, int ns, int device);
+int d4w_fk_plan_destroy(d4w_fk_plan* plan);
+/* describe the plan: info[0]=T1 (row split), [1]=T2, [2]=column tile width in samples,
+ * [3]=column stages, [4]=row stages, [5]=column threads, [6]=row threads, [7]=reserved */
+int d4w_fk_plan_info(const d4w_fk_plan* plan, int* info8);
+
+/* Mask descriptors.  All masks are defined exactly as the reference defines them, in the
+ * fftshift-ed (k, f) layout; the library folds M_sym = (M[k,f] + M[-k,-f]) / 2 (what taking
+ * `.real` at dsp.py:756 amounts to), drops wavenumber rows whose folded mask is identically
+ * zero, scales by 1/(nx*ns) and stores the result in transform order.
+ *
+ * fan: dsp.fk_filter_design (dsp.py:85-171).  kval / fval are numpy's fftfreq steps
+ * 1/(nx*step*dx) and 1/(ns*(1/fs)) computed by the caller in double. */
+int d4w_fk_mask_create_fan(d4w_fk_mask** out, d4w_fk_plan* plan, double kval, double fval,
+                           double cs_min, double cp_min, double cp_max, double cs_max);
+/* hybrid_ninf: dsp.hybrid_ninf_filter_design (dsp.py:308-454).  host_H = the ns-long column
+ * profile built at :348-349 (host pointer, copied); col_lo/col_hi = the column range of
+ * :359-360,:376. */
+int d4w_fk_mask_create_hybrid_ninf(d4w_fk_mask** out, d4w_fk_plan* plan, double kval, double fval,
+                                   double cs_min, double cp_min, double cp_max, double cs_max,
+                                   const double* host_H, int col_lo, int col_hi);
+/* dense: any [nx x ns] mask in the reference's shifted layout, C-order float32 on the device
+ * (design functions without a closed form here, user-made masks).  Synchronises `stream`
+ * once to read back the row support. */
+int d4w_fk_mask_create_dense(d4w_fk_mask** out, d4w_fk_plan* plan, const float* dev_mask_shifted,
+                             void* stream);
+int d4w_fk_mask_destroy(d4w_fk_mask* mask);
+/* rows of the half wavenumber plane (0..nx/2) kept after support pruning */
+int d4w_fk_mask_rows(const d4w_fk_mask* mask);
+/* bytes of device memory the caller must provide for the transform-order table */
+size_t d4w_fk_mask_table_bytes(const d4w_fk_mask* mask);
+/* fill the caller's table (kept by reference until the mask is destroyed) */
+int d4w_fk_mask_build(d4w_fk_mask* mask, float* dev_table, void* stream);
+/* materialise the mask exactly as the reference function returns it: float64 [nx x ns],
+ * shifted layout, C order, into device memory (analytic kinds only) */
+int d4w_fk_mask_materialize(const d4w_fk_mask* mask, double* dev_out, void* stream);
+
+/* bytes of workspace (pruned complex spectrum) the caller must provide for d4w_fk_apply */
+size_t d4w_fk_workspace_bytes(const d4w_fk_plan* plan, const d4w_fk_mask* mask);
+/* y = real(ifft2(ifftshift(fftshift(fft2(x)) * M))) with optional Tukey(alpha=0.03) taper
+ * applied to x first (taper != 0; x itself is not modified).  x, y: float32 [nx x ns],
+ * C order, device memory; y may alias x. */
+int d4w_fk_apply(d4w_fk_plan* plan, d4w_fk_mask* mask, const float* dev_x, float* dev_y,
+                 void* dev_workspace, int taper, void* stream);
+/* the five passes, separately (bench / profiling): pass = 1..5 */
+int d4w_fk_apply_pass(d4w_fk_plan* plan, d4w_fk_mask* mask, const float* dev_x, float* dev_y,
+                      void* dev_workspace, int taper, int pass, void* stream);
+/* D4W_CDEF_END */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* D4W_H */

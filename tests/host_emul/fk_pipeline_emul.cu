@@ -1,0 +1,84 @@
+// CPU emulation of the five f-k passes + mask builders: runs the SAME __host__ __device__
+// kernel bodies as the GPU (fk_kernels.cuh) block by block with nthr = 1.
+// usage: fk_pipeline_emul in.bin out.bin
+//   in.bin : int32 nx, ns, kind, taper, col_lo, col_hi ; float64 kval, fval, c0..c3 ;
+//            float32 x[nx*ns] ; (kind 1: float64 H[ns]) ; (kind 2: float32 mask[nx*ns])
+//   out.bin: float32 y[nx*ns] ; int32 nact
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include "../../das4whales_b200/csrc/fk_hostplan.hpp"
+#include "../../das4whales_b200/csrc/fk_kernels.cuh"
+using namespace d4w;
+
+template <int T1> static void split_all(bool inv, float2* w, size_t ldw, int t2, const float2* twT, int nact) {
+    for (int s = 0; s < nact; ++s)
+        for (int t = 0; t < t2; ++t) {
+            if (inv) body_row_split<T1, true>(w, ldw, t2, twT, s, t);
+            else body_row_split<T1, false>(w, ldw, t2, twT, s, t);
+        }
+}
+static void split_dispatch(int t1, bool inv, float2* w, size_t ldw, int t2, const float2* twT, int nact) {
+    switch (t1) {
+#define C(T) case T: split_all<T>(inv, w, ldw, t2, twT, nact); break;
+        C(2) C(3) C(4) C(5) C(6) C(8) C(10) C(12) C(15) C(16) C(20) C(25)
+#undef C
+        default: fprintf(stderr, "bad t1\n"); exit(2);
+    }
+}
+
+int main(int argc, char** argv) {
+    if (argc < 3) return 2;
+    FILE* fi = fopen(argv[1], "rb");
+    int hdr[6]; double par[6];
+    if (fread(hdr, 4, 6, fi) != 6 || fread(par, 8, 6, fi) != 6) return 3;
+    const int nx = hdr[0], ns = hdr[1], kind = hdr[2], taper = hdr[3];
+    std::vector<float> x((size_t)nx * ns), dense;
+    std::vector<double> H;
+    if (fread(x.data(), 4, x.size(), fi) != x.size()) return 3;
+    if (kind == MASK_HYBRID_NINF) { H.resize(ns); if (fread(H.data(), 8, ns, fi) != (size_t)ns) return 3; }
+    if (kind == MASK_DENSE) { dense.resize((size_t)nx * ns); if (fread(dense.data(), 4, dense.size(), fi) != dense.size()) return 3; }
+    fclose(fi);
+
+    FkHostPlan hp; std::string err;
+    if (build_fk_hostplan(nx, ns, 227 * 1024, hp, err)) { fprintf(stderr, "plan: %s\n", err.c_str()); return 4; }
+    ColParams cp{}; cp.pl = hp.colpl; cp.tw = hp.tw_col.data(); cp.k2pos = hp.k2pos.data(); cp.pos2k = hp.pos2k.data();
+    cp.nx = nx; cp.ns = ns; cp.nc = hp.nc; cp.nc_shift = hp.nc_shift; cp.fstride = hp.fstride; cp.aligned = hp.aligned;
+    RowParams rp{}; rp.pl = hp.rowpl; rp.tw = hp.tw_row.data(); rp.twT = hp.twT.data(); rp.t1 = hp.t1; rp.t2 = hp.t2;
+    MaskParams mp{}; mp.kind = kind; mp.nx = nx; mp.ns = ns; mp.kval = par[0]; mp.fval = par[1];
+    mp.c0 = par[2]; mp.c1 = par[3]; mp.c2 = par[4]; mp.c3 = par[5];
+    mp.h = H.data(); mp.col_lo = hdr[4]; mp.col_hi = hdr[5]; mp.dense = dense.data();
+
+    // support scan
+    const int nrows = nx / 2 + 1;
+    std::vector<unsigned int> rowmax(nrows, 0u);
+    for (int k = 0; k < nrows; ++k) body_mask_rowmax(mp, rowmax.data(), k, 0, ns, 0, 1);
+    std::vector<int> act, k2slot(nrows, -1);
+    for (int k = 0; k < nrows; ++k) { float v; memcpy(&v, &rowmax[k], 4); if (v > 0.f) { k2slot[k] = (int)act.size(); act.push_back(k); } }
+    const int nact = (int)act.size();
+    std::vector<float> tab((size_t)std::max(nact, 1) * ns);
+    const double scale = 1.0 / ((double)nx * ns);
+    for (size_t i = 0; i < (size_t)nact * ns; ++i) body_mask_build(mp, tab.data(), act.data(), hp.pos2k_row.data(), hp.t1, hp.t2, scale, i);
+
+    std::vector<float2> w((size_t)std::max(nact, 1) * ns), smem((size_t)std::max(hp.col_smem, hp.row_smem) / sizeof(float2) + 16);
+    std::vector<float> y((size_t)nx * ns, -777.f);
+    const size_t ldw = ns;
+    const int tile = 2 * hp.nc, ntiles = (ns + tile - 1) / tile;
+    if (nact)
+        for (int b = 0; b < ntiles; ++b)
+            body_col_fwd(cp, x.data(), w.data(), ldw, act.data(), nact, taper ? hp.taper.data() : nullptr, b, 0, 1, smem.data());
+    if (hp.t1 > 1 && nact) split_dispatch(hp.t1, false, w.data(), ldw, hp.t2, hp.twT.data(), nact);
+    for (int s = 0; s < nact; ++s)
+        for (int k1 = 0; k1 < hp.t1; ++k1) body_row_mid(rp, w.data(), ldw, tab.data(), (size_t)ns, k1, s, 0, 1, smem.data());
+    if (hp.t1 > 1 && nact) split_dispatch(hp.t1, true, w.data(), ldw, hp.t2, hp.twT.data(), nact);
+    for (int b = 0; b < ntiles; ++b) body_col_inv(cp, w.data(), ldw, k2slot.data(), y.data(), b, 0, 1, smem.data());
+
+    FILE* fo = fopen(argv[2], "wb");
+    fwrite(y.data(), 4, y.size(), fo);
+    fwrite(&nact, 4, 1, fo);
+    int info[4] = {hp.t1, hp.t2, hp.nc, hp.colpl.nstages};
+    fwrite(info, 4, 4, fo);
+    fclose(fo);
+    return 0;
+}
