@@ -1,0 +1,270 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of das4whales_b200 (contract: see the task statement).
+
+Metric (BASELINE.json): DAS channels/s through the f-k filter, plus achieved HBM GB/s vs the
+measured roofline.  Workload at N=1: BASELINE.json configs[1] -- synthetic 10 000 ch x 120 000
+samp fp32, f-k filter only (dsp.fk_filter_design fan mask), 1 x B200.  At N>1 every rank
+filters its own 10 000 x 120 000 file (the reference path shards by file/channel block with no
+exchange in this mode): weak scaling, no data-path collective.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+NX, NS = 10000, 120000
+DX, FS = 2.0419046878814697, 200.0
+FAN = (1400.0, 1450.0, 3400.0, 3500.0)
+ALGO_BYTES_PER_SAMPLE = 24          # 3 HBM round trips x (read + write) x 4 B
+METRIC = "DAS channels/sec through f-k filter"
+CPU_SAMPLE_NX = 250                 # bounded CPU sample: 250 channels x the full 120 000 samples
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_sample_inputs():
+    import numpy as np
+    rng = np.random.default_rng(1234)
+    return rng.standard_normal((CPU_SAMPLE_NX, NS))
+
+
+def time_cpu_reference(steps, warmup):
+    """The reference's CPU arithmetic (oracle port of dsp.fk_filter_filt, NumPy pocketfft, one
+    thread -- the reference itself is single-threaded) on a bounded sample of the workload."""
+    import numpy as np
+    from oracle import dsp_oracle as O           # allowed here: cpu_baseline / --impl reference legs only
+    x = cpu_sample_inputs()
+    mask = O.fk_filter_design(x.shape, [0, CPU_SAMPLE_NX, 1], DX, FS, *FAN)
+    ts = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        O.fk_filter_filt(x, mask)
+        if i >= warmup:
+            ts.append(time.perf_counter() - t0)
+    t = sum(ts) / len(ts)
+    return CPU_SAMPLE_NX / t, t
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    val, t = time_cpu_reference(steps, warmup)
+    sample = f"{CPU_SAMPLE_NX} ch x {NS} samp float64 per step (1/{NX // CPU_SAMPLE_NX} of the workload's channels, full time axis)"
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "channels/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"synthetic {NX} ch x {NS} samp, f-k filter only (fk_filter_design fan mask)",
+                       "note": "reference CPU path (oracle port of dsp.fk_filter_filt: numpy.fft.fft2 -> mask -> ifft2, "
+                               "complex128, single-threaded like the reference)"},
+            "cpu_baseline": {"value": val, "unit": "channels/s", "cores": 1, "kind": "port", "sample": sample,
+                             "host_cores": os.cpu_count()},
+            "e2e": {"value": val, "unit": "channels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import torch
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import das4whales_b200 as dw
+    from das4whales_b200 import _lib, synth
+    from das4whales_b200.fk import FkFilter
+
+    steps, warmup = max(1, args.steps), max(3, args.warmup)
+    L = _lib.lib()
+    mask = dw.dsp.fk_filter_design((NX, NS), [0, NX, 1], DX, FS, *FAN)
+    flt = FkFilter(mask)
+    x = synth.synth_strain(NX, NS, seed=1234 + rank)
+    y = torch.empty_like(x)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        flt(x, out=y)
+    # ---- per-pass device times (CUDA events on the launching stream) -------------------
+    names = ["p1_col_fwd", "p2_row_split", "p3_row_mid", "p4_row_unsplit", "p5_col_inv"]
+    pass_ms = [0.0] * 5
+    reps = 5
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(6)] for _ in range(reps)]
+    torch.cuda.synchronize()
+    for r in range(reps):
+        ev[r][0].record()
+        for i in range(5):
+            flt.run_pass(i + 1, x, y)
+            ev[r][i + 1].record()
+    torch.cuda.synchronize()
+    for r in range(reps):
+        for i in range(5):
+            pass_ms[i] += ev[r][i].elapsed_time(ev[r][i + 1]) / reps
+
+    # ---- the timed region: exactly K steps ------------------------------------------------
+    sampler = ClockSampler(local)
+    n0 = L.d4w_launch_count()
+    barrier()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        flt(x, out=y)
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = L.d4w_launch_count() - n0
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_step = ms / steps
+    value = NX * world / (ms_step * 1e-3)
+
+    # ---- end to end through the public API with HOST buffers ---------------------------------
+    e2e = None
+    if not args.no_e2e:
+        e2e_steps = min(steps, 5)
+        hx = torch.empty((NX, NS), dtype=torch.float32, pin_memory=True)
+        hy = torch.empty((NX, NS), dtype=torch.float32, pin_memory=True)
+        hx.copy_(x)
+        torch.cuda.synchronize()
+        xd = torch.empty_like(x)
+        for _ in range(1):
+            xd.copy_(hx, non_blocking=True); out = dw.dsp.fk_filter_filt(xd, mask); hy.copy_(out, non_blocking=True)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            xd.copy_(hx, non_blocking=True)              # H2D of this step's strain matrix
+            out = dw.dsp.fk_filter_filt(xd, mask)        # public API (tensor in -> tensor out)
+            hy.copy_(out, non_blocking=True)             # D2H of the filtered matrix
+            torch.cuda.synchronize()
+        barrier()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": NX * world * e2e_steps / dt, "unit": "channels/s", "h2d_bytes_per_step": NX * NS * 4,
+               "d2h_bytes_per_step": NX * NS * 4, "steps": e2e_steps, "ms_per_step": dt / e2e_steps * 1e3,
+               "api": "das4whales_b200.dsp.fk_filter_filt(cuda tensor, FkMask) with pinned-host H2D/D2H each step"}
+        del hx, hy, xd
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        algo_bytes = ALGO_BYTES_PER_SAMPLE * NX * NS
+        achieved = algo_bytes / (ms_step * 1e-3) / 1e9
+        traffic = flt.traffic_bytes()
+        kernels = {n: {"ms": round(pass_ms[i], 4), "actual_bytes": traffic[n],
+                       "actual_gbs": round(traffic[n] / (pass_ms[i] * 1e-3) / 1e9, 1) if pass_ms[i] > 0 else None}
+                   for i, n in enumerate(names)}
+        line = {"metric": METRIC, "value": value, "unit": "channels/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"synthetic {NX} ch x {NS} samp fp32, f-k filter only (fk_filter_design fan mask "
+                                       f"{FAN}), one matrix per GPU",
+                           "l2": "inputs (4.8 GB) exceed the 126 MB L2; no flush needed",
+                           "rows_kept": flt.rows_kept, "rows_total": NX // 2 + 1,
+                           "plan": {"t1": flt.plan.t1, "t2": flt.plan.t2, "col_tile_samples": flt.plan.tile}},
+                "gpu_launches": int(launches),
+                "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                             "frac": round(achieved / peak, 4), "traffic": None,
+                             "peak_source": peak_src,
+                             "scope": "whole f-k filter = 5 kernels per step; achieved = 24 B/(channel*sample) algorithmic bytes "
+                                      "(SURVEY 8d) / step time; actual_bytes per kernel below are lower because wavenumber rows "
+                                      "with an identically-zero folded mask are never stored",
+                             "kernels": kernels},
+                "clocks": clocks}
+        if e2e:
+            line["e2e"] = e2e
+        if not args.no_cpu_baseline and world == 1:
+            cv, ct = time_cpu_reference(steps=1, warmup=0)
+            line["cpu_baseline"] = {"value": cv, "unit": "channels/s", "cores": 1, "kind": "port",
+                                    "sample": f"{CPU_SAMPLE_NX} ch x {NS} samp float64, one fk_filter_filt call ({ct:.1f} s); "
+                                              "oracle port of the reference's numpy.fft path, single-threaded like the reference",
+                                    "host_cores": os.cpu_count()}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

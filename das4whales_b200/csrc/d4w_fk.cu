@@ -35,6 +35,7 @@ struct d4w_fk_plan {
 
 struct d4w_fk_mask {
     d4w_fk_plan* plan = nullptr;
+    int device = 0;
     MaskParams mp{};
     double* d_h = nullptr;
     int nact = 0;
@@ -150,7 +151,7 @@ static int mask_create_common(d4w_fk_mask** out, d4w_fk_plan* plan, const MaskPa
     *out = nullptr;
     DeviceGuard guard(plan->device);
     auto m = new d4w_fk_mask();
-    m->plan = plan; m->mp = mp; m->mp.nx = plan->nx; m->mp.ns = plan->ns;
+    m->plan = plan; m->device = plan->device; m->mp = mp; m->mp.nx = plan->nx; m->mp.ns = plan->ns;
     if (host_h) {
         cudaError_t e = cudaMalloc((void**)&m->d_h, (size_t)plan->ns * sizeof(double));
         if (e == cudaSuccess) e = cudaMemcpy(m->d_h, host_h, (size_t)plan->ns * sizeof(double), cudaMemcpyHostToDevice);
@@ -191,7 +192,7 @@ extern "C" int d4w_fk_mask_create_dense(d4w_fk_mask** out, d4w_fk_plan* plan, co
 
 extern "C" int d4w_fk_mask_destroy(d4w_fk_mask* m) {
     if (!m) return D4W_OK;
-    DeviceGuard guard(m->plan->device);
+    DeviceGuard guard(m->device);
     cudaFree(m->d_h); cudaFree(m->d_act_k); cudaFree(m->d_k2slot);
     delete m;
     return D4W_OK;

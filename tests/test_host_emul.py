@@ -1,0 +1,89 @@
+"""CPU: the SAME __host__ __device__ kernel bodies the GPU runs (csrc/fk_kernels.cuh,
+fft_smem.cuh) executed block-by-block on the host and checked against the oracle.  Catches
+indexing / twiddle / fold / untangle errors without a GPU."""
+import os
+import shutil
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+import scipy.signal as sps
+
+from oracle import dsp_oracle as O
+from conftest import rel_err, ROOT
+
+NVCC = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+pytestmark = pytest.mark.skipif(not os.path.exists(NVCC), reason="nvcc not available")
+EMUL = os.path.join(ROOT, "tests", "host_emul")
+DX, FS = 2.0419046878814697, 200.0
+
+
+def _build(name, tmp):
+    exe = os.path.join(tmp, name)
+    r = subprocess.run([NVCC, "-std=c++17", "-O2", "--expt-relaxed-constexpr", "-Wno-deprecated-gpu-targets",
+                        "-o", exe, os.path.join(EMUL, name + ".cu")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr + r.stdout
+    return exe
+
+
+@pytest.fixture(scope="module")
+def tmpdir_mod(tmp_path_factory):
+    return str(tmp_path_factory.mktemp("emul"))
+
+
+def test_fft_engine_emulation(tmpdir_mod):
+    exe = _build("fft_engine_emul", tmpdir_mod)
+    for maxr in ("25", "16", "8"):
+        r = subprocess.run([exe, maxr], capture_output=True, text=True)
+        assert r.returncode == 0 and "OK" in r.stdout, r.stdout
+
+
+def _run(exe, tmp, nx, ns, kind, taper, x, kval, fval, c, H=None, dense=None, col=(0, 0), env=None):
+    fin, fout = os.path.join(tmp, "in.bin"), os.path.join(tmp, "out.bin")
+    with open(fin, "wb") as f:
+        f.write(struct.pack("6i", nx, ns, kind, int(taper), col[0], col[1]))
+        f.write(struct.pack("6d", kval, fval, *c))
+        f.write(x.astype(np.float32).tobytes())
+        if kind == 1:
+            f.write(np.asarray(H, dtype=np.float64).tobytes())
+        if kind == 2:
+            f.write(np.asarray(dense, dtype=np.float32).tobytes())
+    e = dict(os.environ)
+    e.update(env or {})
+    subprocess.run([exe, fin, fout], check=True, env=e)
+    raw = open(fout, "rb").read()
+    return np.frombuffer(raw[: nx * ns * 4], dtype=np.float32).reshape(nx, ns), struct.unpack("5i", raw[nx * ns * 4:])
+
+
+CASES = [(40, 240, 1, False, None), (45, 175, 1, True, None), (38, 120, 2, False, None),
+         (100, 1200, 1, True, {"D4W_T1": "12"}), (30, 600, 1, False, {"D4W_T1": "5", "D4W_COL_NC": "1"}),
+         (250, 360, 1, False, {"D4W_T1": "6", "D4W_COL_NC": "4"})]
+
+
+def test_fk_pipeline_emulation(tmpdir_mod):
+    exe = _build("fk_pipeline_emul", tmpdir_mod)
+    rng = np.random.default_rng(0)
+    for nx, ns, step, taper, env in CASES:
+        x32 = rng.standard_normal((nx, ns)).astype(np.float32)
+        x64 = x32.astype(np.float64)
+        sel = [0, nx * step, step]
+        kval, fval = 1.0 / (nx * (step * DX)), 1.0 / (ns * (1 / FS))
+        c = (1400., 1450., 3400., 3500.)
+        M = O.fk_filter_design((nx, ns), sel, DX, FS, *c)
+        ref = O.fk_filter_filt(x64.copy(), M, tapering=taper)
+        y, tail = _run(exe, tmpdir_mod, nx, ns, 0, taper, x32, kval, fval, c, env=env)
+        assert 0 < tail[0] < nx // 2 + 1, "fan mask support must prune wavenumber rows"
+        assert rel_err(y, ref)[0] <= 5e-6, (nx, ns, "fan")
+        y2, _ = _run(exe, tmpdir_mod, nx, ns, 2, taper, x32, kval, fval, c, dense=np.ascontiguousarray(M), env=env)
+        assert rel_err(y2, ref)[0] <= 5e-6, (nx, ns, "dense")
+        if ns % 2 == 0:
+            cc = (1350., 1450., 3300., 3450.)
+            Mh = O.hybrid_ninf_filter_design((nx, ns), sel, DX, FS, *cc, 14., 30.)
+            freq = np.fft.fftshift(np.fft.fftfreq(ns, d=1 / FS))
+            b, a = sps.butter(8, [14 / (FS / 2), 30 / (FS / 2)], "bp")
+            H = np.concatenate((np.zeros(ns // 2), np.abs(sps.freqz(b, a, worN=ns // 2)[1]) ** 2))
+            i0, i1 = int(np.argmax(freq >= 0)), int(np.argmax(freq >= 44))
+            refh = O.fk_filter_filt(x64.copy(), Mh, tapering=taper)
+            yh, _ = _run(exe, tmpdir_mod, nx, ns, 1, taper, x32, kval, fval, cc, H=H, col=(i0, i1), env=env)
+            assert rel_err(yh, refh)[0] <= 5e-6, (nx, ns, "hybrid_ninf")

@@ -1,0 +1,118 @@
+"""CPU: the oracle restatement against the committed golden vectors (outputs of the
+UNMODIFIED reference, tests/golden/, made by oracle/make_golden.py) and -- when
+/root/reference is present -- against the live reference."""
+import numpy as np
+import pytest
+
+from oracle import dsp_oracle as O, detect_oracle as D, ref_loader
+from conftest import rel_err
+
+DX = 2.0419046878814697
+FS = 200.0
+
+
+def test_masks_match_golden(golden):
+    g = golden("masks")
+    for key in g.files:
+        kind, shape = key.split("_")[0], key.split("_")[1]
+        nx, ns = (int(v) for v in shape.split("x"))
+        step = int(key.split("_s")[1]) if "_s" in key else 1
+        sel = [0, nx * step, step]
+        if kind == "fan":
+            m = O.fk_filter_design((nx, ns), sel, DX, FS, 1400, 1450, 3400, 3500)
+        elif kind == "ninf":
+            m = O.hybrid_ninf_filter_design((nx, ns), sel, DX, FS, 1350., 1450., 3300, 3450, 14., 30.)
+        else:
+            m = O.hybrid_filter_design((nx, ns), sel, DX, FS, 1400., 1450., 15., 25.)
+        assert np.max(np.abs(m - g[key])) <= 1e-13, key
+
+
+def test_fk_apply_matches_golden(golden):
+    g, gm = golden("fk_apply"), golden("masks")
+    for tag in ("fan_even", "fan_odd", "fan_p19", "ninf_even", "hyb_even"):
+        x, y = g[tag + "_x"], g[tag + "_y"]
+        m = gm[str(g[tag + "_mask"])]
+        taper = bool(g[tag + "_taper"])
+        assert rel_err(O.fk_filter_filt(x.copy(), m, tapering=taper), y)[0] <= 1e-12
+        # folded half-spectrum identity the CUDA path is built on
+        assert rel_err(O.fk_filter_filt_rows(x.copy(), m, np.arange(x.shape[0]), tapering=taper), y)[0] <= 1e-10
+
+
+def test_reference_known_answers(golden):
+    # reference tests/test_dsp.py:85-88 and :136-141
+    t = O.taper_data(np.array([[1., 2, 3, 4, 5], [1, 2, 3, 4, 5]]))
+    assert np.array_equal(t, golden("fk_apply")["kat_taper"])
+    assert np.array_equal(t, np.array([[0., 2, 3, 4, 0], [0, 2, 3, 4, 0]]))
+    s = golden("snr")
+    out = O.snr_tr_array(s["kat_in"])
+    assert np.allclose(out[0], [-3.01029996, 3.01029996, 6.53212514, 9.03089987, 10.96910013])
+    assert rel_err(out, s["kat"])[0] <= 1e-14
+
+
+def test_iir_and_snr_match_golden(golden):
+    g = golden("iir")
+    assert rel_err(O.bp_filt(g["bp_x"], FS, 14, 30), g["bp_y"])[0] <= 1e-12
+    assert rel_err(O.sosfiltfilt(g["sos_bp5"], g["bp_x"]), g["sos_bp5_y"])[0] <= 1e-12
+    assert rel_err(O.butterworth_filter([5, [10, 30], "bp"], FS), g["sos_bp5"])[0] <= 1e-14
+    s = golden("snr")
+    for env in (0, 1):
+        a, b = O.snr_tr_array(s["x"], env=bool(env)), s[f"snr_env{env}"]
+        assert np.max(np.abs(a - b)) <= 1e-9
+
+
+def test_matched_filter_matches_golden(golden):
+    g = golden("matched_filter")
+    x = g["x"]
+    time = np.arange(x.shape[1]) / FS
+    for tag, (f0, f1, dur) in {"hf": (17.8, 28.8, 0.68), "lf": (14.7, 21.8, 0.78)}.items():
+        tpl = D.gen_template_fincall(time, FS, f0, f1, dur)
+        assert rel_err(tpl, g["tpl_" + tag])[0] <= 1e-14
+        assert rel_err(D.compute_cross_correlogram(x, tpl), g["corr_" + tag])[0] <= 1e-12
+        assert rel_err(D.compute_cross_correlogram_direct(x, tpl), g["corr_" + tag])[0] <= 1e-10
+        assert rel_err(D.envelope(g["corr_" + tag]), g["env_" + tag])[0] <= 1e-12
+        picks = D.convert_pick_times(D.pick_times_env(g["corr_" + tag], 0.05))
+        assert np.array_equal(picks, g["picks_" + tag])
+    assert rel_err(D.gen_linear_chirp(15., 25., 1.0, FS), g["lin_chirp"])[0] <= 1e-14
+    a = np.array([1., 2, 3, 4, 5]); b = np.array([2., 1, 0, -1, 2])
+    assert rel_err(D.shift_xcorr(a, b), g["sx"])[0] <= 1e-14
+    assert rel_err(D.shift_nxcorr(a, b), g["snx"])[0] <= 1e-14
+
+
+def test_spectrocorr_pieces_match_golden(golden):
+    g = golden("spectrocorr")
+    _, _, ker = D.buildkernel(27., 16., 4., 0.9, g["ff"], g["tt"], FS, 12., 36.)
+    assert rel_err(ker, g["ker"])[0] <= 1e-14
+    assert rel_err(D.xcorr2d(g["S"], g["ker"]), g["xc2d"])[0] <= 1e-12
+
+
+def test_stft_restatement_against_scipy():
+    """librosa is not installed anywhere here; pin the restated STFT against
+    SciPy's independent implementation with the same framing."""
+    import scipy.signal as sps
+    rng = np.random.default_rng(0)
+    y = rng.standard_normal(3000)
+    for n_fft, hop in ((128, 25), (256, 12), (160, 8)):
+        s = O.stft_librosa(y, n_fft, hop)
+        _, _, z = sps.stft(y, nperseg=n_fft, noverlap=n_fft - hop, window=sps.get_window("hann", n_fft, fftbins=True),
+                           boundary="zeros", padded=False, return_onesided=True, scaling="spectrum")
+        z = z * sps.get_window("hann", n_fft, fftbins=True).sum()     # undo scipy's 1/sum(w) scaling
+        n = min(s.shape[1], z.shape[1])
+        assert n >= 1 + (len(y) - n_fft) // hop
+        assert rel_err(np.abs(s[:, :n]), np.abs(z[:, :n]))[0] <= 1e-10
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="/root/reference not present (GPU box)")
+def test_oracle_against_live_reference():
+    dsp, detect = ref_loader.load()
+    rng = np.random.default_rng(5)
+    nx, ns = 36, 200
+    x = rng.standard_normal((nx, ns))
+    sel = [0, nx, 1]
+    m = dsp.fk_filter_design((nx, ns), sel, DX, FS)
+    assert np.array_equal(m, O.fk_filter_design((nx, ns), sel, DX, FS))
+    assert rel_err(O.fk_filter_filt(x.copy(), m, True), dsp.fk_filter_filt(x.copy(), m, True))[0] <= 1e-13
+    h = np.asarray(dsp.hybrid_ninf_filter_design((nx, ns), sel, DX, FS))
+    assert np.max(np.abs(h - O.hybrid_ninf_filter_design((nx, ns), sel, DX, FS))) <= 1e-13
+    assert rel_err(O.bp_filt(x, FS, 14, 30), dsp.bp_filt(x, FS, 14, 30))[0] <= 1e-13
+    tpl = detect.gen_template_fincall(np.arange(ns) / FS, FS, 17.8, 28.8, 0.68)
+    assert rel_err(D.compute_cross_correlogram(x, tpl), detect.compute_cross_correlogram(x, tpl))[0] <= 1e-13
