@@ -1,0 +1,232 @@
+// d4w_rows.cu -- host side of the per-channel operators (C ABI in include/d4w.h).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include "d4w_common.hpp"
+#include "fk_hostplan.hpp"
+#include "rows_kernels.cuh"
+
+using namespace d4w;
+
+// ------------------------------------------------------------------ generic smem FFT plan (xcorr blocks, STFT frames)
+struct d4w_fft_plan {
+    int n = 0, device = 0;
+    FftPlan pl{};
+    std::vector<int> pos2k;
+    float2* d_tw = nullptr;
+    int* d_k2pos = nullptr;
+};
+
+extern "C" int d4w_fft_plan_create(d4w_fft_plan** out, int n, int device) {
+    if (!out) return fail(D4W_ERR_ARG, "d4w_fft_plan_create: null output");
+    *out = nullptr;
+    if (n < 2) return fail(D4W_ERR_ARG, "d4w_fft_plan_create: n must be >= 2");
+    DeviceGuard guard(device);
+    auto p = new d4w_fft_plan();
+    p->n = n; p->device = device;
+    std::string err;
+    if (!make_plan(n, env_int("D4W_ROW_MAX_RADIX", 16), p->pl, err)) { delete p; return fail(D4W_ERR_UNSUPPORTED, err); }
+    p->pos2k = make_pos2freq(p->pl);
+    std::vector<int> k2pos((size_t)n);
+    for (int i = 0; i < n; ++i) k2pos[p->pos2k[i]] = i;
+    cudaError_t e = upload(&p->d_tw, make_twiddles(n));
+    if (e == cudaSuccess) e = upload(&p->d_k2pos, k2pos);
+    if (e != cudaSuccess) { d4w_fft_plan_destroy(p); return fail(D4W_ERR_CUDA, std::string("fft plan: ") + cudaGetErrorString(e)); }
+    *out = p;
+    return D4W_OK;
+}
+
+extern "C" int d4w_fft_plan_destroy(d4w_fft_plan* p) {
+    if (!p) return D4W_OK;
+    DeviceGuard guard(p->device);
+    cudaFree(p->d_tw); cudaFree(p->d_k2pos);
+    delete p;
+    return D4W_OK;
+}
+
+extern "C" int d4w_fft_plan_order(const d4w_fft_plan* p, int* host_pos2freq) {
+    if (!p || !host_pos2freq) return fail(D4W_ERR_ARG, "d4w_fft_plan_order: null argument");
+    std::memcpy(host_pos2freq, p->pos2k.data(), (size_t)p->n * sizeof(int));
+    return D4W_OK;
+}
+
+// ------------------------------------------------------------------ row statistics / plain SNR
+extern "C" int d4w_row_stats(const float* x, int nx, int ns, int seglen, double* stats, double* segpre, void* stream) {
+    if (!x || !stats || nx < 1 || ns < 1) return fail(D4W_ERR_ARG, "d4w_row_stats: bad argument");
+    int nseg = 0;
+    if (segpre) {
+        if (seglen < 1) return fail(D4W_ERR_ARG, "d4w_row_stats: seglen must be >= 1 when segpre is given");
+        nseg = (ns + seglen - 1) / seglen;
+        if (nseg > kMaxSeg) return fail(D4W_ERR_UNSUPPORTED, "d4w_row_stats: more than 512 segments per row");
+    }
+    k_row_stats<<<nx, 256, 0, (cudaStream_t)stream>>>(x, ns, seglen, nseg, stats, segpre);
+    D4W_CHECK_LAUNCH("k_row_stats");
+    return D4W_OK;
+}
+
+extern "C" int d4w_snr(const float* x, float* out, int nx, int ns, const double* stats, void* stream) {
+    if (!x || !out || !stats) return fail(D4W_ERR_ARG, "d4w_snr: null argument");
+    const size_t total = (size_t)nx * ns;
+    const size_t blocks = (total + 255) / 256;
+    if (blocks > 0x7fffffffull) return fail(D4W_ERR_UNSUPPORTED, "d4w_snr: matrix too large");
+    k_snr_plain<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, out, ns, stats, total);
+    D4W_CHECK_LAUNCH("k_snr_plain");
+    return D4W_OK;
+}
+
+// ------------------------------------------------------------------ overlap-save matched filter
+extern "C" int d4w_xcorr(d4w_fft_plan* p, const float* x, int nx, int ns, int valid, int ntpl, const void* dev_tabs,
+                         const double* dev_mu_over_m, const double* dev_stats, const double* dev_segpre, float* out,
+                         void* stream) {
+    if (!p || !x || !dev_tabs || !out) return fail(D4W_ERR_ARG, "d4w_xcorr: null argument");
+    if (valid < 1 || valid > p->n || ntpl < 1) return fail(D4W_ERR_ARG, "d4w_xcorr: bad valid / ntpl");
+    const bool normalize = dev_stats != nullptr;
+    if (normalize && (!dev_segpre || !dev_mu_over_m)) return fail(D4W_ERR_ARG, "d4w_xcorr: normalisation needs stats, segpre and mu");
+    DeviceGuard guard(p->device);
+    XcorrParams xp{};
+    xp.pl = p->pl; xp.tw = p->d_tw; xp.nb = p->n; xp.valid = valid; xp.ntpl = ntpl; xp.ns = ns;
+    xp.normalize = normalize ? 1 : 0;
+    xp.nseg = (ns + valid - 1) / valid;
+    const size_t smem = (size_t)3 * p->n * sizeof(float2);
+    D4W_CUDA_TRY(cudaFuncSetAttribute(k_xcorr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((xp.nseg + 1) / 2, nx);
+    k_xcorr<<<grid, 256, smem, (cudaStream_t)stream>>>(xp, x, (const float2*)dev_tabs, dev_stats, dev_segpre, dev_mu_over_m, out,
+                                                      (size_t)nx * ns);
+    D4W_CHECK_LAUNCH("k_xcorr");
+    return D4W_OK;
+}
+
+// ------------------------------------------------------------------ Hilbert envelope / envelope SNR
+struct d4w_row_plan {
+    int ns = 0, device = 0, t1 = 1, t2 = 0;
+    RowParams row{};
+    float2 *d_tw = nullptr, *d_twT = nullptr;
+    float* d_hilbert = nullptr;
+    size_t row_smem = 0;
+};
+
+extern "C" int d4w_row_plan_create(d4w_row_plan** out, int ns, int device) {
+    if (!out) return fail(D4W_ERR_ARG, "d4w_row_plan_create: null output");
+    *out = nullptr;
+    if (ns < 1) return fail(D4W_ERR_ARG, "d4w_row_plan_create: ns must be >= 1");
+    DeviceGuard guard(device);
+    cudaDeviceProp prop;
+    D4W_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    FkHostPlan hp; std::string err;
+    if (build_fk_hostplan(1, ns, prop.sharedMemPerBlockOptin, hp, err)) return fail(D4W_ERR_UNSUPPORTED, err);
+    auto p = new d4w_row_plan();
+    p->ns = ns; p->device = device; p->t1 = hp.t1; p->t2 = hp.t2; p->row_smem = hp.row_smem;
+    p->row.pl = hp.rowpl; p->row.t1 = hp.t1; p->row.t2 = hp.t2;
+    // analytic-signal weights of scipy.signal.hilbert (N = ns, no padding), scaled by 1/ns, transform order
+    std::vector<float> h((size_t)ns);
+    for (int kt1 = 0; kt1 < hp.t1; ++kt1)
+        for (int pos = 0; pos < hp.t2; ++pos) {
+            const int f = kt1 + hp.t1 * hp.pos2k_row[pos];
+            double wgt;
+            if (ns % 2 == 0) wgt = (f == 0 || f == ns / 2) ? 1.0 : (f < ns / 2 ? 2.0 : 0.0);
+            else wgt = (f == 0) ? 1.0 : (f <= (ns - 1) / 2 ? 2.0 : 0.0);
+            h[(size_t)kt1 * hp.t2 + pos] = (float)(wgt / ns);
+        }
+    cudaError_t e = upload(&p->d_tw, hp.tw_row);
+    if (e == cudaSuccess) e = upload(&p->d_twT, hp.twT);
+    if (e == cudaSuccess) e = upload(&p->d_hilbert, h);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_row_mid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->row_smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_hilbert_row, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->row_smem);
+    if (e != cudaSuccess) { d4w_row_plan_destroy(p); return fail(D4W_ERR_CUDA, std::string("row plan: ") + cudaGetErrorString(e)); }
+    p->row.tw = p->d_tw; p->row.twT = p->d_twT;
+    *out = p;
+    return D4W_OK;
+}
+
+extern "C" int d4w_row_plan_destroy(d4w_row_plan* p) {
+    if (!p) return D4W_OK;
+    DeviceGuard guard(p->device);
+    cudaFree(p->d_tw); cudaFree(p->d_twT); cudaFree(p->d_hilbert);
+    delete p;
+    return D4W_OK;
+}
+
+extern "C" size_t d4w_row_workspace_bytes(const d4w_row_plan* p, int nx) {
+    if (!p || p->t1 == 1) return 16;
+    return (size_t)nx * p->ns * sizeof(float2);
+}
+
+extern "C" int d4w_hilbert(d4w_row_plan* p, const float* x, float* out, int nx, void* workspace, int mode,
+                           const double* dev_stats, void* stream_v) {
+    if (!p || !x || !out || nx < 1) return fail(D4W_ERR_ARG, "d4w_hilbert: bad argument");
+    if (mode == EPI_SNR && !dev_stats) return fail(D4W_ERR_ARG, "d4w_hilbert: SNR mode needs row statistics");
+    if (nx > 65535 && p->t1 > 1) return fail(D4W_ERR_UNSUPPORTED, "d4w_hilbert: more than 65535 rows per call");
+    DeviceGuard guard(p->device);
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    if (p->t1 == 1) {
+        k_hilbert_row<<<nx, 256, p->row_smem, stream>>>(p->row, x, out, p->d_hilbert, mode, dev_stats);
+        D4W_CHECK_LAUNCH("k_hilbert_row");
+        return D4W_OK;
+    }
+    if (!workspace) return fail(D4W_ERR_ARG, "d4w_hilbert: workspace required for split rows");
+    float2* w = (float2*)workspace;
+    const int threads = 128;
+    dim3 grid((p->t2 + threads - 1) / threads, nx);
+    switch (p->t1) {
+#define D4W_HC(T) case T: k_hsplit_fwd<T><<<grid, threads, 0, stream>>>(x, p->ns, w, p->t2, p->d_twT); break;
+        D4W_HC(2) D4W_HC(3) D4W_HC(4) D4W_HC(5) D4W_HC(6) D4W_HC(8) D4W_HC(10) D4W_HC(12) D4W_HC(15) D4W_HC(16) D4W_HC(20) D4W_HC(25)
+#undef D4W_HC
+        default: return fail(D4W_ERR_UNSUPPORTED, "row split radix not built");
+    }
+    D4W_CHECK_LAUNCH("k_hsplit_fwd");
+    dim3 gmid(p->t1, nx);
+    k_row_mid<<<gmid, 256, p->row_smem, stream>>>(p->row, w, (size_t)p->ns, p->d_hilbert, (size_t)0);
+    D4W_CHECK_LAUNCH("k_row_mid");
+    switch (p->t1) {
+#define D4W_HC(T) case T: k_hsplit_inv<T><<<grid, threads, 0, stream>>>(w, p->ns, out, p->t2, p->d_twT, mode, dev_stats); break;
+        D4W_HC(2) D4W_HC(3) D4W_HC(4) D4W_HC(5) D4W_HC(6) D4W_HC(8) D4W_HC(10) D4W_HC(12) D4W_HC(15) D4W_HC(16) D4W_HC(20) D4W_HC(25)
+#undef D4W_HC
+        default: return fail(D4W_ERR_UNSUPPORTED, "row split radix not built");
+    }
+    D4W_CHECK_LAUNCH("k_hsplit_inv");
+    return D4W_OK;
+}
+
+// ------------------------------------------------------------------ forward-backward SOS IIR
+extern "C" int d4w_sosfiltfilt(const float* x, float* y, float* tmp, int nx, int ns, const double* host_sos,
+                               const double* host_zi, int nsec, int padlen, void* stream_v) {
+    if (!x || !y || !tmp || !host_sos || !host_zi) return fail(D4W_ERR_ARG, "d4w_sosfiltfilt: null argument");
+    if (nsec < 1 || nsec > kMaxSections) return fail(D4W_ERR_UNSUPPORTED, "d4w_sosfiltfilt: 1..16 sections supported");
+    if (padlen < 0 || ns <= padlen) return fail(D4W_ERR_ARG, "The length of the input vector x must be greater than padlen");
+    SosParams sp{};
+    for (int s = 0; s < nsec; ++s) {
+        const double* c = host_sos + 6 * s;
+        const double a0 = c[3];
+        sp.b0[s] = c[0] / a0; sp.b1[s] = c[1] / a0; sp.b2[s] = c[2] / a0; sp.a1[s] = c[4] / a0; sp.a2[s] = c[5] / a0;
+        sp.zi0[s] = host_zi[2 * s]; sp.zi1[s] = host_zi[2 * s + 1];
+    }
+    sp.nsec = nsec; sp.pad = padlen; sp.ns = ns;
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    const int blocks = (nx + 31) / 32;
+    k_sos_pass<1><<<blocks, 32, 0, stream>>>(sp, x, tmp, y, nx);
+    D4W_CHECK_LAUNCH("k_sos_pass<fwd>");
+    k_sos_pass<-1><<<blocks, 32, 0, stream>>>(sp, x, tmp, y, nx);
+    D4W_CHECK_LAUNCH("k_sos_pass<bwd>");
+    return D4W_OK;
+}
+
+// ------------------------------------------------------------------ batched STFT magnitude
+extern "C" int d4w_stft_mag(d4w_fft_plan* p, const float* x, float* out, int nx, int ns, int hop, const float* dev_window,
+                            void* stream_v) {
+    if (!p || !x || !out || !dev_window) return fail(D4W_ERR_ARG, "d4w_stft_mag: null argument");
+    if (p->n % 2 || hop < 1) return fail(D4W_ERR_ARG, "d4w_stft_mag: n_fft must be even and hop >= 1");
+    if (nx > 65535) return fail(D4W_ERR_UNSUPPORTED, "d4w_stft_mag: more than 65535 rows per call");
+    DeviceGuard guard(p->device);
+    StftParams sp{};
+    sp.pl = p->pl; sp.tw = p->d_tw; sp.k2pos = p->d_k2pos;
+    sp.nfft = p->n; sp.hop = hop; sp.ns = ns; sp.nframes = 1 + ns / hop; sp.nbins = p->n / 2 + 1;
+    int fpb = 32;
+    while (fpb > 2 && (size_t)(fpb / 2) * (p->n + 1) * sizeof(float2) > 96 * 1024) fpb >>= 1;
+    sp.fpb = fpb;
+    const size_t smem = (size_t)(fpb / 2) * (p->n + 1) * sizeof(float2);
+    D4W_CUDA_TRY(cudaFuncSetAttribute(k_stft_mag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((sp.nframes + fpb - 1) / fpb, nx);
+    k_stft_mag<<<grid, 256, smem, (cudaStream_t)stream_v>>>(sp, x, dev_window, out);
+    D4W_CHECK_LAUNCH("k_stft_mag");
+    return D4W_OK;
+}

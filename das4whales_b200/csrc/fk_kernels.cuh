@@ -246,43 +246,43 @@ __host__ __device__ inline void body_row_mid(const RowParams& rp, float2* __rest
 #ifdef __CUDACC__
 extern __shared__ float2 d4w_dyn_smem[];
 
-__global__ void __launch_bounds__(256, 1)
+static __global__ void __launch_bounds__(256, 1)
 k_col_fwd(ColParams cp, const float* __restrict__ x, float2* __restrict__ w, size_t ldw, const int* __restrict__ act_k,
           int nact, const float* __restrict__ taper) {
     body_col_fwd(cp, x, w, ldw, act_k, nact, taper, blockIdx.x, threadIdx.x, blockDim.x, d4w_dyn_smem);
 }
 
-__global__ void __launch_bounds__(256, 1)
+static __global__ void __launch_bounds__(256, 1)
 k_col_inv(ColParams cp, const float2* __restrict__ w, size_t ldw, const int* __restrict__ k2slot, float* __restrict__ y) {
     body_col_inv(cp, w, ldw, k2slot, y, blockIdx.x, threadIdx.x, blockDim.x, d4w_dyn_smem);
 }
 
 template <int T1, bool INV>
-__global__ void __launch_bounds__(128)
+static __global__ void __launch_bounds__(128)
 k_row_split(float2* __restrict__ w, size_t ldw, int t2len, const float2* __restrict__ twT) {
     const int t2 = blockIdx.x * blockDim.x + threadIdx.x;
     if (t2 < t2len) body_row_split<T1, INV>(w, ldw, t2len, twT, blockIdx.y, t2);
 }
 
-__global__ void __launch_bounds__(256, 2)
+static __global__ void __launch_bounds__(256, 2)
 k_row_mid(RowParams rp, float2* __restrict__ w, size_t ldw, const float* __restrict__ tab, size_t tab_slot_stride) {
     body_row_mid(rp, w, ldw, tab, tab_slot_stride, blockIdx.x, blockIdx.y, threadIdx.x, blockDim.x, d4w_dyn_smem);
 }
 
-__global__ void k_mask_rowmax(MaskParams mp, unsigned int* rowmax, int fchunk) {
+static __global__ void k_mask_rowmax(MaskParams mp, unsigned int* rowmax, int fchunk) {
     const int k = blockIdx.y;
     const int f0 = blockIdx.x * fchunk;
     const int f1 = min(mp.ns, f0 + fchunk);
     body_mask_rowmax(mp, rowmax, k, f0, f1, threadIdx.x, blockDim.x);
 }
 
-__global__ void k_mask_build(MaskParams mp, float* tab, const int* act_k, const int* pos2k_row, int t1, int t2,
+static __global__ void k_mask_build(MaskParams mp, float* tab, const int* act_k, const int* pos2k_row, int t1, int t2,
                              double scale, size_t total) {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx < total) body_mask_build(mp, tab, act_k, pos2k_row, t1, t2, scale, idx);
 }
 
-__global__ void k_mask_materialize(MaskParams mp, double* out, size_t total) {
+static __global__ void k_mask_materialize(MaskParams mp, double* out, size_t total) {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx < total) out[idx] = mask_shifted(mp, (int)(idx / mp.ns), (int)(idx % mp.ns));
 }

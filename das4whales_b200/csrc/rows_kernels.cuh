@@ -1,0 +1,362 @@
+// rows_kernels.cuh -- per-channel (row) operators: statistics, overlap-save matched filter,
+// Hilbert envelope / SNR, forward-backward SOS IIR, batched STFT magnitude.
+//
+// Reference arithmetic replaced (files under /root/reference/src/das4whales/):
+//   detect.compute_cross_correlogram / shift_xcorr          detect.py:96-166
+//   dsp.snr_tr_array, |scipy.signal.hilbert| (pick_times_env) dsp.py:956-976, detect.py:192
+//   dsp.bp_filt (scipy filtfilt) and caller-side sosfiltfilt dsp.py:859-880, Example.py:55
+//   dsp.get_spectrogram / detect.get_sliced_nspectrogram     dsp.py:41-78, detect.py:334-408
+#pragma once
+#include "fft_smem.cuh"
+#include "fk_kernels.cuh"
+
+namespace d4w {
+
+// ------------------------------------------------------------------ row statistics
+// stats[row] = {mean, absmax, population variance, 0}; optional segpre[row][s] = sum over
+// samples before segment s of (x - mean)/absmax  (prefix of the normalised row, for the
+// matched filter's mean-of-padded-template term).
+constexpr int kMaxSeg = 512;
+
+static __global__ void __launch_bounds__(256)
+k_row_stats(const float* __restrict__ x, int ns, int seglen, int nseg, double* __restrict__ stats,
+            double* __restrict__ segpre) {
+    __shared__ double s_sum[8], s_sq[8];
+    __shared__ float s_max[8];
+    __shared__ double s_seg[kMaxSeg];
+    const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const float* r = x + (size_t)row * ns;
+    double sum = 0.0, sq = 0.0;
+    float mx = 0.f;
+    if (segpre) for (int s = tid; s < nseg; s += blockDim.x) s_seg[s] = 0.0;
+    __syncthreads();
+    if (segpre) {
+        // one warp per segment keeps the per-segment sums exact and atomic-free
+        for (int s = wid; s < nseg; s += 8) {
+            const int a = s * seglen, b = min(ns, a + seglen);
+            double ss = 0.0;
+            for (int i = a + lane; i < b; i += 32) {
+                const float v = r[i];
+                ss += (double)v; sq += (double)v * (double)v; mx = fmaxf(mx, fabsf(v));
+            }
+            for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+            if (lane == 0) s_seg[s] = ss;
+            sum += ss / 32.0;     // every lane adds 1/32 of the warp total -> warp reduction below restores it
+        }
+    } else {
+        for (int i = tid; i < ns; i += blockDim.x) {
+            const float v = r[i];
+            sum += (double)v; sq += (double)v * (double)v; mx = fmaxf(mx, fabsf(v));
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if (lane == 0) { s_sum[wid] = sum; s_sq[wid] = sq; s_max[wid] = mx; }
+    __syncthreads();
+    if (tid == 0) {
+        double S = 0.0, Q = 0.0; float M = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { S += s_sum[w]; Q += s_sq[w]; M = fmaxf(M, s_max[w]); }
+        const double mean = S / ns;
+        double var = Q / ns - mean * mean;
+        if (var < 0.0) var = 0.0;
+        stats[4 * (size_t)row + 0] = mean;
+        stats[4 * (size_t)row + 1] = (double)M;
+        stats[4 * (size_t)row + 2] = var;
+        stats[4 * (size_t)row + 3] = 0.0;
+        if (segpre) {
+            double acc = 0.0;
+            for (int s = 0; s < nseg; ++s) {
+                segpre[(size_t)row * nseg + s] = acc;
+                const int len = min(ns, (s + 1) * seglen) - s * seglen;
+                acc += (s_seg[s] - mean * len) / (double)M;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ SNR (no envelope)
+static __global__ void k_snr_plain(const float* __restrict__ x, float* __restrict__ out, int ns, const double* __restrict__ stats,
+                            size_t total) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const size_t row = i / ns;
+    const float var = (float)stats[4 * row + 2];
+    const float v = x[i];
+    out[i] = 10.0f * log10f(v * v / var);                 // dsp.py:976 (zeros give -inf like the reference)
+}
+
+// ------------------------------------------------------------------ overlap-save matched filter
+// One block = two consecutive segments of one channel packed as re/im of one complex FFT of
+// length nb (correlation with a real template is real-linear, so no untangling is needed):
+//   S = FFT(seg);  for each template: IFFT(S * conj(C_t)/nb/m_t) -> valid = nb - L + 1 lags.
+// tabs[t][p] holds conj(C_t[k(p)]) / (nb * m_t) in transform order.
+struct XcorrParams {
+    FftPlan pl;
+    const float2* tw;
+    int nb, valid, ntpl, ns, normalize, nseg;
+};
+
+static __global__ void __launch_bounds__(256, 2)
+k_xcorr(XcorrParams xp, const float* __restrict__ x, const float2* __restrict__ tabs, const double* __restrict__ stats,
+        const double* __restrict__ segpre, const double* __restrict__ mu_over_m, float* __restrict__ out, size_t out_tpl_stride) {
+    extern __shared__ float2 sm[];
+    float2* S = sm;                   // spectrum of the segment pair
+    float2* B = sm + xp.nb;           // work buffer for the inverse
+    float2* P = sm + 2 * xp.nb;       // exclusive prefix sums of the normalised samples (valid entries)
+    __shared__ float2 s_wsum[8];
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, wid = tid >> 5;
+    const int row = blockIdx.y;
+    const int seg_a = 2 * blockIdx.x, seg_b = seg_a + 1;
+    const int ns = xp.ns, nb = xp.nb, V = xp.valid;
+    const int ta = seg_a * V, tb = seg_b * V;
+    const float* r = x + (size_t)row * ns;
+    float mean = 0.f, inv = 1.f;
+    if (xp.normalize) { mean = (float)stats[4 * (size_t)row]; inv = (float)(1.0 / stats[4 * (size_t)row + 1]); }
+    for (int i = tid; i < nb; i += nthr) {
+        const int ia = ta + i, ib = tb + i;
+        const float a = (ia < ns) ? (r[ia] - mean) * inv : 0.f;
+        const float b = (ib < ns) ? (r[ib] - mean) * inv : 0.f;
+        S[i] = make_float2(a, b);
+    }
+    __syncthreads();
+    // exclusive prefix of the first V samples of each segment (only needed for the mu term)
+    if (xp.normalize) {
+        const int chunk = (V + nthr - 1) / nthr;
+        const int i0 = min(V, tid * chunk), i1 = min(V, i0 + chunk);
+        float2 loc = make_float2(0.f, 0.f);
+        for (int i = i0; i < i1; ++i) { loc.x += S[i].x; loc.y += S[i].y; }
+        float2 inc = loc;
+        for (int o = 1; o < 32; o <<= 1) {
+            const float ux = __shfl_up_sync(0xffffffffu, inc.x, o), uy = __shfl_up_sync(0xffffffffu, inc.y, o);
+            if (lane >= o) { inc.x += ux; inc.y += uy; }
+        }
+        if (lane == 31) s_wsum[wid] = inc;
+        __syncthreads();
+        float2 base = make_float2(0.f, 0.f);
+        for (int w = 0; w < wid; ++w) { base.x += s_wsum[w].x; base.y += s_wsum[w].y; }
+        float2 run = make_float2(base.x + inc.x - loc.x, base.y + inc.y - loc.y);
+        const float pa = (seg_a < xp.nseg) ? (float)segpre[(size_t)row * xp.nseg + seg_a] : 0.f;
+        const float pb = (seg_b < xp.nseg) ? (float)segpre[(size_t)row * xp.nseg + seg_b] : 0.f;
+        for (int i = i0; i < i1; ++i) {
+            P[i] = make_float2(pa + run.x, pb + run.y);
+            run.x += S[i].x; run.y += S[i].y;
+        }
+        __syncthreads();
+    }
+    fft_forward_stages(S, xp.pl, xp.tw, 1, nb, tid, nthr, 0, xp.pl.nstages);
+    for (int t = 0; t < xp.ntpl; ++t) {
+        const float2* tab = tabs + (size_t)t * nb;
+        for (int i = tid; i < nb; i += nthr) B[i] = cmul(S[i], tab[i]);
+        __syncthreads();
+        fft_inverse_stages(B, xp.pl, xp.tw, 1, nb, tid, nthr, 0, xp.pl.nstages);
+        const float mu = xp.normalize ? (float)mu_over_m[t] : 0.f;
+        float* o = out + (size_t)t * out_tpl_stride + (size_t)row * ns;
+        for (int i = tid; i < V; i += nthr) {
+            const float2 v = B[i];
+            float2 p = make_float2(0.f, 0.f);
+            if (xp.normalize) p = P[i];
+            // out = (sum x~ c - mu * suffix) / m, suffix = -prefix because x~ sums to zero
+            if (ta + i < ns) o[ta + i] = v.x + mu * p.x;
+            if (tb + i < ns) o[tb + i] = v.y + mu * p.y;
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------ Hilbert envelope / SNR on the T1 x T2 row engine
+enum { EPI_ENV = 0, EPI_SNR = 1 };
+
+__device__ __forceinline__ float hilbert_epilogue(float2 z, int mode, float var) {
+    const float p = z.x * z.x + z.y * z.y;
+    return mode == EPI_ENV ? sqrtf(p) : 10.0f * log10f(p / var);
+}
+
+// forward split reading the REAL row (imag = 0) and writing the complex workspace
+template <int T1>
+static __global__ void __launch_bounds__(128)
+k_hsplit_fwd(const float* __restrict__ x, int ns, float2* __restrict__ w, int t2len, const float2* __restrict__ twT) {
+    const int t2 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t2 >= t2len) return;
+    const size_t row = blockIdx.y;
+    const float* src = x + row * ns + t2;
+    float2 v[T1];
+    static_for<T1>([&](auto jc) { constexpr int j = decltype(jc)::value; v[j] = make_float2(src[(size_t)j * t2len], 0.f); });
+    float2 p[T1];
+    twiddle_powers<T1>(twT[t2], p);
+    DFT<T1, false>::run(v);
+    float2* dst = w + row * ns + t2;
+    static_for<T1>([&](auto jc) {
+        constexpr int j = decltype(jc)::value;
+        dst[(size_t)j * t2len] = (j > 0) ? cmul(v[j], p[j]) : v[j];
+    });
+}
+
+// inverse split reading the complex workspace and writing |z| or the envelope SNR
+template <int T1>
+static __global__ void __launch_bounds__(128)
+k_hsplit_inv(const float2* __restrict__ w, int ns, float* __restrict__ out, int t2len, const float2* __restrict__ twT, int mode,
+             const double* __restrict__ stats) {
+    const int t2 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t2 >= t2len) return;
+    const size_t row = blockIdx.y;
+    const float2* src = w + row * ns + t2;
+    float2 v[T1];
+    static_for<T1>([&](auto jc) { constexpr int j = decltype(jc)::value; v[j] = src[(size_t)j * t2len]; });
+    float2 p[T1];
+    twiddle_powers<T1>(twT[t2], p);
+    static_for<T1>([&](auto jc) { constexpr int j = decltype(jc)::value; if constexpr (j > 0) v[j] = cmulc(v[j], p[j]); });
+    DFT<T1, true>::run(v);
+    const float var = (mode == EPI_SNR) ? (float)stats[4 * row + 2] : 1.f;
+    float* dst = out + row * ns + t2;
+    static_for<T1>([&](auto jc) { constexpr int j = decltype(jc)::value; dst[(size_t)j * t2len] = hilbert_epilogue(v[j], mode, var); });
+}
+
+// whole row in one CTA (T1 == 1): real in -> FFT -> weights -> IFFT -> epilogue out
+static __global__ void __launch_bounds__(256, 2)
+k_hilbert_row(RowParams rp, const float* __restrict__ x, float* __restrict__ out, const float* __restrict__ tab, int mode,
+              const double* __restrict__ stats) {
+    extern __shared__ float2 sm[];
+    const int n = rp.t2, tid = threadIdx.x, nthr = blockDim.x;
+    const size_t row = blockIdx.x;
+    const float* src = x + row * n;
+    for (int i = tid; i < n; i += nthr) sm[i] = make_float2(src[i], 0.f);
+    __syncthreads();
+    fft_forward_stages(sm, rp.pl, rp.tw, 1, n, tid, nthr, 0, rp.pl.nstages);
+    for (int i = tid; i < n; i += nthr) { const float s = tab[i]; float2 v = sm[i]; v.x *= s; v.y *= s; sm[i] = v; }
+    __syncthreads();
+    fft_inverse_stages(sm, rp.pl, rp.tw, 1, n, tid, nthr, 0, rp.pl.nstages);
+    const float var = (mode == EPI_SNR) ? (float)stats[4 * row + 2] : 1.f;
+    float* dst = out + row * n;
+    for (int i = tid; i < n; i += nthr) dst[i] = hilbert_epilogue(sm[i], mode, var);
+}
+
+// ------------------------------------------------------------------ forward-backward SOS IIR (scipy sosfiltfilt semantics)
+constexpr int kMaxSections = 16;
+struct SosParams {
+    double b0[kMaxSections], b1[kMaxSections], b2[kMaxSections], a1[kMaxSections], a2[kMaxSections];
+    double zi0[kMaxSections], zi1[kMaxSections];
+    int nsec, pad, ns;
+};
+
+// value of the odd-extended signal at extended index e in [0, ns + 2*pad)
+__device__ __forceinline__ float ext_value(const float* __restrict__ r, int e, int pad, int ns) {
+    const int i = e - pad;
+    if (i < 0) return 2.f * r[0] - r[-i];
+    if (i >= ns) return 2.f * r[ns - 1] - r[2 * (ns - 1) - i];
+    return r[i];
+}
+
+// One warp = 32 channels; time is walked in tiles of 32 samples staged through shared memory so
+// global accesses stay coalesced while each lane runs its channel's recursion in double.
+// DIR = +1: forward pass over the extended signal, writes tmp[nx][next];
+// DIR = -1: backward pass over tmp, writes the central ns samples to y.
+template <int DIR>
+static __global__ void __launch_bounds__(32)
+k_sos_pass(SosParams sp, const float* __restrict__ x, float* __restrict__ tmp, float* __restrict__ y, int nx) {
+    __shared__ float tile[32][33];
+    const int lane = threadIdx.x;
+    const int ch0 = blockIdx.x * 32;
+    const int ns = sp.ns, pad = sp.pad, next = ns + 2 * pad;
+    const int ch = ch0 + lane;
+    const bool live = ch < nx;
+    double z0[kMaxSections], z1[kMaxSections];
+    // initial state: zi * first sample of the sequence being filtered (scipy sosfiltfilt)
+    float first = 0.f;
+    if (live) {
+        if (DIR > 0) first = ext_value(x + (size_t)ch * ns, 0, pad, ns);
+        else first = tmp[(size_t)ch * next + (next - 1)];
+    }
+#pragma unroll
+    for (int s = 0; s < kMaxSections; ++s) { z0[s] = sp.zi0[s] * (double)first; z1[s] = sp.zi1[s] * (double)first; }
+    const int ntiles = (next + 31) / 32;
+    for (int tix = 0; tix < ntiles; ++tix) {
+        const int e0 = (DIR > 0) ? tix * 32 : next - 32 * (tix + 1);     // tile covers e0 .. e0+31 (may start < 0)
+        // stage in: lane = time, loop over channels
+        for (int c = 0; c < 32; ++c) {
+            const int cc = ch0 + c;
+            const int e = e0 + lane;
+            float v = 0.f;
+            if (cc < nx && e >= 0 && e < next) v = (DIR > 0) ? ext_value(x + (size_t)cc * ns, e, pad, ns) : tmp[(size_t)cc * next + e];
+            tile[c][lane] = v;
+        }
+        __syncwarp();
+        if (live) {
+            for (int q = 0; q < 32; ++q) {
+                const int k = (DIR > 0) ? q : 31 - q;
+                const int e = e0 + k;
+                if (e < 0 || e >= next) continue;
+                double v = (double)tile[lane][k];
+#pragma unroll
+                for (int s = 0; s < kMaxSections; ++s) {
+                    if (s < sp.nsec) {
+                        const double o = fma(sp.b0[s], v, z0[s]);
+                        z0[s] = fma(sp.b1[s], v, fma(-sp.a1[s], o, z1[s]));
+                        z1[s] = fma(sp.b2[s], v, -sp.a2[s] * o);
+                        v = o;
+                    }
+                }
+                tile[lane][k] = (float)v;
+            }
+        }
+        __syncwarp();
+        for (int c = 0; c < 32; ++c) {
+            const int cc = ch0 + c;
+            const int e = e0 + lane;
+            if (cc < nx && e >= 0 && e < next) {
+                if (DIR > 0) tmp[(size_t)cc * next + e] = tile[c][lane];
+                else { const int i = e - pad; if (i >= 0 && i < ns) y[(size_t)cc * ns + i] = tile[c][lane]; }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------ batched STFT magnitude (librosa.stft framing)
+// Frame m covers samples m*hop - nfft/2 + [0, nfft) of the zero-padded row, times the periodic
+// Hann window; two frames share one complex FFT (re / im) and are untangled afterwards.
+struct StftParams {
+    FftPlan pl;
+    const float2* tw;
+    const int* k2pos;
+    int nfft, hop, ns, nframes, nbins, fpb;      // fpb = frames per block (even)
+};
+
+static __global__ void __launch_bounds__(256)
+k_stft_mag(StftParams sp, const float* __restrict__ x, const float* __restrict__ win, float* __restrict__ out) {
+    extern __shared__ float2 sm[];
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int n = sp.nfft, half = n / 2;
+    const size_t row = blockIdx.y;
+    const int m0 = blockIdx.x * sp.fpb;
+    const int npair = sp.fpb / 2, fstride = n + 1;
+    const float* r = x + row * sp.ns;
+    for (int i = tid; i < npair * n; i += nthr) {
+        const int q = i / n, j = i - q * n;
+        const int ma = m0 + 2 * q, mb = ma + 1;
+        const int ia = ma * sp.hop + j - half, ib = mb * sp.hop + j - half;
+        const float w = win[j];
+        const float a = (ma < sp.nframes && ia >= 0 && ia < sp.ns) ? r[ia] * w : 0.f;
+        const float b = (mb < sp.nframes && ib >= 0 && ib < sp.ns) ? r[ib] * w : 0.f;
+        sm[q * fstride + j] = make_float2(a, b);
+    }
+    __syncthreads();
+    fft_forward_stages(sm, sp.pl, sp.tw, npair, fstride, tid, nthr, 0, sp.pl.nstages);
+    float* o = out + row * (size_t)sp.nbins * sp.nframes;
+    for (int i = tid; i < sp.nbins * sp.fpb; i += nthr) {
+        const int k = i / sp.fpb, f = i - k * sp.fpb;          // frame fastest -> contiguous stores
+        const int m = m0 + f;
+        if (m >= sp.nframes) continue;
+        const int q = f >> 1;
+        const float2 z = sm[q * fstride + sp.k2pos[k]];
+        const float2 z2 = sm[q * fstride + sp.k2pos[k == 0 ? 0 : n - k]];
+        float2 v;
+        if ((f & 1) == 0) v = make_float2(0.5f * (z.x + z2.x), 0.5f * (z.y - z2.y));
+        else              v = make_float2(0.5f * (z.y + z2.y), 0.5f * (z2.x - z.x));
+        o[(size_t)k * sp.nframes + m] = sqrtf(v.x * v.x + v.y * v.y);
+    }
+}
+
+}  // namespace d4w

@@ -1,29 +1,219 @@
 """Per-channel (row) operators on the GPU: row statistics, overlap-save matched filter, Hilbert
-envelope / SNR, forward-backward SOS IIR, batched STFT.  Thin host wrappers over libd4w.so."""
+envelope / SNR, forward-backward SOS IIR, batched STFT.  Thin host wrappers over libd4w.so
+(csrc/rows_kernels.cuh); inputs are contiguous float32 CUDA tensors [nx, ns]."""
 import numpy as np
+import scipy.signal as sp
 
 from . import _lib
 
-
-def _nyi(name):
-    raise _lib.D4WError(f"das4whales_b200.rows.{name}: kernel not built yet")
-
-
-def sosfiltfilt(sos, x, padlen=None):
-    _nyi("sosfiltfilt")
+_fft_plans = {}
+_row_plans = {}
+_tab_cache = {}
 
 
-def stft_mag(x, nfft, hop):
-    _nyi("stft_mag")
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise _lib.D4WError("das4whales_b200 needs a CUDA device (no CPU fallback)")
+    return torch
 
 
-def snr(x, env=False):
-    _nyi("snr")
+def _check_input(x):
+    torch = _torch()
+    if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.ndim == 2):
+        raise ValueError("expected a contiguous float32 CUDA tensor [channels, samples]")
+    return x.device.index
+
+
+class _FftPlan:
+    def __init__(self, n, device):
+        L = _lib.lib()
+        out = _lib.ffi.new("d4w_fft_plan**")
+        _lib.check(L.d4w_fft_plan_create(out, int(n), int(device)), f"fft plan n={n}")
+        self.ptr, self.n = out[0], int(n)
+        order = np.empty(n, dtype=np.int32)
+        _lib.check(L.d4w_fft_plan_order(self.ptr, _lib.ffi.cast("int*", order.ctypes.data)), "fft order")
+        self.pos2freq = order
+
+
+def fft_plan(n, device):
+    key = (int(n), int(device))
+    if key not in _fft_plans:
+        _fft_plans[key] = _FftPlan(*key)
+    return _fft_plans[key]
+
+
+class _RowPlan:
+    def __init__(self, ns, device):
+        L = _lib.lib()
+        out = _lib.ffi.new("d4w_row_plan**")
+        _lib.check(L.d4w_row_plan_create(out, int(ns), int(device)), f"row plan ns={ns}")
+        self.ptr, self.ns, self.device = out[0], int(ns), int(device)
+
+
+def row_plan(ns, device):
+    key = (int(ns), int(device))
+    if key not in _row_plans:
+        _row_plans[key] = _RowPlan(*key)
+    return _row_plans[key]
+
+
+# ------------------------------------------------------------------------------ statistics
+def row_stats(x, seglen=0):
+    """-> (stats [nx,4] float64 = mean, absmax, var, 0 ; segpre [nx,nseg] float64 or None)"""
+    torch = _torch()
+    dev = _check_input(x)
+    nx, ns = x.shape
+    stats = torch.empty((nx, 4), dtype=torch.float64, device=x.device)
+    segpre = None
+    if seglen:
+        nseg = (ns + seglen - 1) // seglen
+        segpre = torch.empty((nx, nseg), dtype=torch.float64, device=x.device)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().d4w_row_stats(_lib.ptr(x, "float*"), nx, ns, int(seglen), _lib.ptr(stats, "double*"),
+                                            _lib.ptr(segpre, "double*") if segpre is not None else _lib.ffi.NULL,
+                                            _lib.stream_ptr()), "row_stats")
+    return stats, segpre
+
+
+# ------------------------------------------------------------------------------ matched filter
+def _pick_block(L):
+    for nb in (1024, 2048, 4096, 8192):
+        if nb >= 4 * L or (nb == 8192 and nb >= L + 1):
+            return nb
+    raise ValueError(f"template with {L} taps is too long for the overlap-save matched filter (max 8191)")
+
+
+def cross_correlogram(x, templates, normalize=True):
+    """Positive-lag correlation of every row with each template (detect.py:96-166).
+    templates: list of 1-D float64 arrays (zero-padded to ns, as gen_template_fincall returns).
+    Returns a list of float32 CUDA tensors [nx, ns]."""
+    torch = _torch()
+    dev = _check_input(x)
+    nx, ns = x.shape
+    taps, mus, ms = [], [], []
+    for t in templates:
+        t = np.asarray(t, dtype=np.float64).ravel()
+        if len(t) != ns and normalize:
+            raise ValueError(f"template length {len(t)} != number of samples {ns}")
+        nz = np.nonzero(t)[0]
+        L = int(nz[-1]) + 1 if len(nz) else 1
+        c = t[:L]
+        if normalize:
+            m = float(np.max(np.abs(t)))              # detect.py:158: abs-max of the un-demeaned template
+            mu = float(np.sum(c) / len(t))            # mean of the PADDED template
+            taps.append(c - mu)                       # taps of (template - mean) inside the support ...
+            mus.append(mu / m)                        # ... and -mu/m outside it (handled as a prefix-sum term)
+            ms.append(m)
+        else:
+            taps.append(c); mus.append(0.0); ms.append(1.0)
+    Lmax = max(len(c) for c in taps)
+    nb = _pick_block(Lmax)
+    valid = nb - Lmax + 1
+    plan = fft_plan(nb, dev)
+    tabs = np.empty((len(taps), nb), dtype=np.complex64)
+    for i, (c, m) in enumerate(zip(taps, ms)):
+        spec = np.fft.fft(c, nb)
+        tabs[i] = (np.conj(spec) / (nb * m))[plan.pos2freq]
+    out = torch.empty((len(taps), nx, ns), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(dev):
+        tabs_d = torch.from_numpy(tabs.view(np.float32).reshape(len(taps), nb, 2)).to(x.device)
+        null = _lib.ffi.NULL
+        if normalize:
+            stats, segpre = row_stats(x, seglen=valid)
+            mu_d = torch.tensor(mus, dtype=torch.float64, device=x.device)
+            a_mu, a_st, a_sp = _lib.ptr(mu_d, "double*"), _lib.ptr(stats, "double*"), _lib.ptr(segpre, "double*")
+        else:
+            a_mu = a_st = a_sp = null
+        _lib.check(_lib.lib().d4w_xcorr(plan.ptr, _lib.ptr(x, "float*"), nx, ns, valid, len(taps), _lib.ptr(tabs_d),
+                                        a_mu, a_st, a_sp, _lib.ptr(out, "float*"), _lib.stream_ptr()), "xcorr")
+    return [out[i] for i in range(len(taps))]
+
+
+# ------------------------------------------------------------------------------ Hilbert envelope / SNR
+def _hilbert(x, mode, stats=None):
+    torch = _torch()
+    dev = _check_input(x)
+    nx, ns = x.shape
+    plan = row_plan(ns, dev)
+    out = torch.empty_like(x)
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        # rows are independent: chunk so the complex workspace stays bounded (and gridDim.y <= 65535)
+        max_rows = max(1, min(65535, (8 << 30) // (ns * 8)))
+        wsb = L.d4w_row_workspace_bytes(plan.ptr, min(nx, max_rows))
+        ws = torch.empty(int(wsb), dtype=torch.uint8, device=x.device)
+        for r0 in range(0, nx, max_rows):
+            r1 = min(nx, r0 + max_rows)
+            st = _lib.ptr(stats[r0:r1], "double*") if stats is not None else _lib.ffi.NULL
+            _lib.check(L.d4w_hilbert(plan.ptr, _lib.ptr(x[r0:r1], "float*"), _lib.ptr(out[r0:r1], "float*"), r1 - r0,
+                                     _lib.ptr(ws), int(mode), st, _lib.stream_ptr()), "hilbert")
+    return out
 
 
 def envelope(x):
-    _nyi("envelope")
+    """|scipy.signal.hilbert(x, axis=1)|"""
+    return _hilbert(x, 0)
 
 
-def cross_correlogram(x, templates):
-    _nyi("cross_correlogram")
+def snr(x, env=False):
+    """dsp.snr_tr_array (dsp.py:956-976)"""
+    torch = _torch()
+    dev = _check_input(x)
+    stats, _ = row_stats(x)
+    if env:
+        return _hilbert(x, 1, stats)
+    out = torch.empty_like(x)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().d4w_snr(_lib.ptr(x, "float*"), _lib.ptr(out, "float*"), x.shape[0], x.shape[1],
+                                      _lib.ptr(stats, "double*"), _lib.stream_ptr()), "snr")
+    return out
+
+
+# ------------------------------------------------------------------------------ zero-phase SOS IIR
+def sosfiltfilt(sos, x, padlen=None):
+    """scipy.signal.sosfiltfilt(sos, x, axis=1) semantics (odd extension, sosfilt_zi initial
+    state); padlen=None uses SciPy's default, bp_filt passes filtfilt's 3*max(len(a),len(b))."""
+    torch = _torch()
+    dev = _check_input(x)
+    sos = np.ascontiguousarray(sos, dtype=np.float64)
+    if sos.ndim != 2 or sos.shape[1] != 6:
+        raise ValueError("sos must have shape (n_sections, 6)")
+    nsec = sos.shape[0]
+    if padlen is None:
+        ntaps = 2 * nsec + 1
+        ntaps -= min((sos[:, 2] == 0).sum(), (sos[:, 5] == 0).sum())
+        padlen = 3 * ntaps
+    nx, ns = x.shape
+    if ns <= padlen:
+        raise ValueError(f"The length of the input vector x must be greater than padlen, which is {padlen}.")
+    zi = np.ascontiguousarray(sp.sosfilt_zi(sos), dtype=np.float64)
+    y = torch.empty_like(x)
+    tmp = torch.empty((nx, ns + 2 * padlen), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().d4w_sosfiltfilt(_lib.ptr(x, "float*"), _lib.ptr(y, "float*"), _lib.ptr(tmp, "float*"), nx, ns,
+                                              _lib.ffi.cast("double*", sos.ctypes.data), _lib.ffi.cast("double*", zi.ctypes.data),
+                                              nsec, int(padlen), _lib.stream_ptr()), "sosfiltfilt")
+    return y
+
+
+# ------------------------------------------------------------------------------ STFT magnitude
+def stft_mag(x, nfft, hop):
+    """|librosa.stft(y, n_fft=nfft, hop_length=hop)| for every row -> [nx, 1+nfft/2, 1+ns//hop]"""
+    torch = _torch()
+    dev = _check_input(x)
+    nx, ns = x.shape
+    plan = fft_plan(nfft, dev)
+    nframes = 1 + ns // hop
+    out = torch.empty((nx, nfft // 2 + 1, nframes), dtype=torch.float32, device=x.device)
+    key = ("hann", nfft, dev)
+    if key not in _tab_cache:
+        _tab_cache[key] = torch.from_numpy(sp.get_window("hann", nfft, fftbins=True).astype(np.float32)).to(x.device)
+    win = _tab_cache[key]
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        for r0 in range(0, nx, 65535):
+            r1 = min(nx, r0 + 65535)
+            _lib.check(L.d4w_stft_mag(plan.ptr, _lib.ptr(x[r0:r1], "float*"), _lib.ptr(out[r0:r1], "float*"), r1 - r0, ns,
+                                      int(hop), _lib.ptr(win, "float*"), _lib.stream_ptr()), "stft_mag")
+    return out

@@ -89,6 +89,54 @@ int d4w_fk_apply(d4w_fk_plan* plan, d4w_fk_mask* mask, const float* dev_x, float
 /* the five passes, separately (bench / profiling): pass = 1..5 */
 int d4w_fk_apply_pass(d4w_fk_plan* plan, d4w_fk_mask* mask, const float* dev_x, float* dev_y,
                       void* dev_workspace, int taper, int pass, void* stream);
+
+/* ---- generic shared-memory FFT plan (matched-filter blocks, STFT frames) ----------------- */
+typedef struct d4w_fft_plan d4w_fft_plan;
+typedef struct d4w_row_plan d4w_row_plan;
+int d4w_fft_plan_create(d4w_fft_plan** out, int n, int device);
+int d4w_fft_plan_destroy(d4w_fft_plan* plan);
+/* host_pos2freq[p] = DFT bin stored at position p after the forward transform (n ints) */
+int d4w_fft_plan_order(const d4w_fft_plan* plan, int* host_pos2freq);
+
+/* ---- row statistics: np.mean / np.max(np.abs) / np.std(axis=1) used by
+ *      detect.compute_cross_correlogram (detect.py:157) and dsp.snr_tr_array (dsp.py:975-976).
+ *      dev_stats: double[nx][4] = {mean, absmax, population variance, 0}.  dev_segpre (optional):
+ *      double[nx][ceil(ns/seglen)], prefix sums of the normalised row at segment starts. */
+int d4w_row_stats(const float* dev_x, int nx, int ns, int seglen, double* dev_stats, double* dev_segpre,
+                  void* stream);
+/* dsp.snr_tr_array(trace, env=False) (dsp.py:976): 10*log10(x^2 / var_row) */
+int d4w_snr(const float* dev_x, float* dev_out, int nx, int ns, const double* dev_stats, void* stream);
+
+/* ---- matched filter: detect.compute_cross_correlogram / shift_xcorr (detect.py:96-166) as
+ *      overlap-save FFT correlation; `plan` = fft plan of the block length nb, `valid` = nb - L + 1
+ *      lags kept per block.  dev_tabs: ntpl x nb complex64 = conj(FFT_nb(template_t)) / (nb * m_t) in
+ *      the plan's transform order.  With dev_stats != NULL rows are demeaned / peak-normalised and
+ *      the mean-of-padded-template term mu_t/m_t * prefix is added (dev_mu_over_m: double[ntpl]).
+ *      dev_out: float32 [ntpl][nx][ns]. */
+int d4w_xcorr(d4w_fft_plan* plan, const float* dev_x, int nx, int ns, int valid, int ntpl, const void* dev_tabs,
+              const double* dev_mu_over_m, const double* dev_stats, const double* dev_segpre, float* dev_out,
+              void* stream);
+
+/* ---- Hilbert envelope |scipy.signal.hilbert(x, axis=1)| (detect.py:192) and
+ *      dsp.snr_tr_array(trace, env=True) (dsp.py:975).  mode 0: envelope, 1: 10*log10(env^2/var). */
+int d4w_row_plan_create(d4w_row_plan** out, int ns, int device);
+int d4w_row_plan_destroy(d4w_row_plan* plan);
+size_t d4w_row_workspace_bytes(const d4w_row_plan* plan, int nx);
+int d4w_hilbert(d4w_row_plan* plan, const float* dev_x, float* dev_out, int nx, void* dev_workspace, int mode,
+                const double* dev_stats, void* stream);
+
+/* ---- zero-phase IIR: dsp.bp_filt = scipy.signal.filtfilt (dsp.py:859-880) and the caller-side
+ *      scipy.signal.sosfiltfilt(sos, trace, axis=1) (Example.py:55).  host_sos: double[nsec][6],
+ *      host_zi: double[nsec][2] (scipy.signal.sosfilt_zi), odd extension of padlen samples,
+ *      dev_tmp: float32 [nx][ns + 2*padlen]. */
+int d4w_sosfiltfilt(const float* dev_x, float* dev_y, float* dev_tmp, int nx, int ns, const double* host_sos,
+                    const double* host_zi, int nsec, int padlen, void* stream);
+
+/* ---- batched STFT magnitude with librosa.stft framing (dsp.get_spectrogram dsp.py:66-68,
+ *      detect.get_sliced_nspectrogram detect.py:382): centred frames, zero padding, window
+ *      dev_window[n_fft]; dev_out: float32 [nx][n_fft/2+1][1 + ns/hop]. */
+int d4w_stft_mag(d4w_fft_plan* plan, const float* dev_x, float* dev_out, int nx, int ns, int hop,
+                 const float* dev_window, void* stream);
 /* D4W_CDEF_END */
 
 #ifdef __cplusplus
