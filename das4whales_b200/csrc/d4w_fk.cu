@@ -80,9 +80,10 @@ extern "C" int d4w_fk_plan_create(d4w_fk_plan** out, int nx, int ns, int device)
     if (e == cudaSuccess) e = upload(&pl->d_k2pos, k2p);
     if (e == cudaSuccess) e = upload(&pl->d_pos2k_row, p2kr);
     if (e == cudaSuccess) e = upload(&pl->d_taper, tap);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_col_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->col_smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_col_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->col_smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_row_mid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->row_smem);
+    // the attribute is per-kernel global state: always raise it to the device maximum, never to a plan's own size
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_col_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_col_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_row_mid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
     if (e != cudaSuccess) {
         std::string msg = std::string("d4w_fk_plan_create: ") + cudaGetErrorString(e);
         d4w_fk_plan_destroy(pl);

@@ -11,6 +11,7 @@ using namespace d4w;
 // ------------------------------------------------------------------ generic smem FFT plan (xcorr blocks, STFT frames)
 struct d4w_fft_plan {
     int n = 0, device = 0;
+    size_t smem_cap = 0;
     FftPlan pl{};
     std::vector<int> pos2k;
     float2* d_tw = nullptr;
@@ -22,8 +23,10 @@ extern "C" int d4w_fft_plan_create(d4w_fft_plan** out, int n, int device) {
     *out = nullptr;
     if (n < 2) return fail(D4W_ERR_ARG, "d4w_fft_plan_create: n must be >= 2");
     DeviceGuard guard(device);
+    cudaDeviceProp prop;
+    D4W_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     auto p = new d4w_fft_plan();
-    p->n = n; p->device = device;
+    p->n = n; p->device = device; p->smem_cap = prop.sharedMemPerBlockOptin;
     std::string err;
     if (!make_plan(n, env_int("D4W_ROW_MAX_RADIX", 16), p->pl, err)) { delete p; return fail(D4W_ERR_UNSUPPORTED, err); }
     p->pos2k = make_pos2freq(p->pl);
@@ -88,7 +91,8 @@ extern "C" int d4w_xcorr(d4w_fft_plan* p, const float* x, int nx, int ns, int va
     xp.normalize = normalize ? 1 : 0;
     xp.nseg = (ns + valid - 1) / valid;
     const size_t smem = (size_t)3 * p->n * sizeof(float2);
-    D4W_CUDA_TRY(cudaFuncSetAttribute(k_xcorr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > p->smem_cap) return fail(D4W_ERR_UNSUPPORTED, "d4w_xcorr: block length too large for shared memory");
+    D4W_CUDA_TRY(cudaFuncSetAttribute(k_xcorr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_cap));
     dim3 grid((xp.nseg + 1) / 2, nx);
     k_xcorr<<<grid, 256, smem, (cudaStream_t)stream>>>(xp, x, (const float2*)dev_tabs, dev_stats, dev_segpre, dev_mu_over_m, out,
                                                       (size_t)nx * ns);
@@ -130,8 +134,8 @@ extern "C" int d4w_row_plan_create(d4w_row_plan** out, int ns, int device) {
     cudaError_t e = upload(&p->d_tw, hp.tw_row);
     if (e == cudaSuccess) e = upload(&p->d_twT, hp.twT);
     if (e == cudaSuccess) e = upload(&p->d_hilbert, h);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_row_mid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->row_smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_hilbert_row, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->row_smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_row_mid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_hilbert_row, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin);
     if (e != cudaSuccess) { d4w_row_plan_destroy(p); return fail(D4W_ERR_CUDA, std::string("row plan: ") + cudaGetErrorString(e)); }
     p->row.tw = p->d_tw; p->row.twT = p->d_twT;
     *out = p;
@@ -224,7 +228,8 @@ extern "C" int d4w_stft_mag(d4w_fft_plan* p, const float* x, float* out, int nx,
     while (fpb > 2 && (size_t)(fpb / 2) * (p->n + 1) * sizeof(float2) > 96 * 1024) fpb >>= 1;
     sp.fpb = fpb;
     const size_t smem = (size_t)(fpb / 2) * (p->n + 1) * sizeof(float2);
-    D4W_CUDA_TRY(cudaFuncSetAttribute(k_stft_mag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > p->smem_cap) return fail(D4W_ERR_UNSUPPORTED, "d4w_stft_mag: n_fft too large for shared memory");
+    D4W_CUDA_TRY(cudaFuncSetAttribute(k_stft_mag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_cap));
     dim3 grid((sp.nframes + fpb - 1) / fpb, nx);
     k_stft_mag<<<grid, 256, smem, (cudaStream_t)stream_v>>>(sp, x, dev_window, out);
     D4W_CHECK_LAUNCH("k_stft_mag");

@@ -1,0 +1,134 @@
+"""GPU parity tests for the per-channel operators (matched filter, envelope / SNR, zero-phase
+IIR, STFT) against the golden vectors of the unmodified reference and the float64 oracle.
+Contract tolerance: max-norm relative error <= 1e-4 (fp32 kernels)."""
+import numpy as np
+import pytest
+
+from conftest import rel_err
+from oracle import dsp_oracle as O, detect_oracle as D
+
+pytestmark = pytest.mark.gpu
+FS = 200.0
+TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def dw():
+    import torch
+    assert torch.cuda.is_available()
+    import das4whales_b200 as dw
+    from das4whales_b200 import _lib
+    _lib.lib()
+    return dw
+
+
+def test_cross_correlogram_golden(dw, golden):
+    g = golden("matched_filter")
+    x = g["x"]
+    for tag in ("hf", "lf"):
+        out = dw.detect.compute_cross_correlogram(x, g["tpl_" + tag])
+        assert out.shape == x.shape and out.dtype == np.float64
+        e = rel_err(out, g["corr_" + tag])
+        assert e[0] <= 2e-5, (tag, e)
+    both = dw.detect.compute_cross_correlograms(x, [g["tpl_hf"], g["tpl_lf"]])
+    assert rel_err(both[0], g["corr_hf"])[0] <= 2e-5 and rel_err(both[1], g["corr_lf"])[0] <= 2e-5
+    a = np.array([1., 2, 3, 4, 5]); b = np.array([2., 1, 0, -1, 2])
+    assert rel_err(dw.detect.shift_xcorr(a, b), g["sx"])[0] <= 1e-5
+    assert rel_err(dw.detect.shift_nxcorr(a, b), g["snx"])[0] <= 1e-5
+
+
+@pytest.mark.parametrize("nx,ns", [(7, 1500), (33, 12000), (5, 120000)])
+def test_cross_correlogram_vs_oracle(dw, nx, ns):
+    rng = np.random.default_rng(ns)
+    x = (rng.standard_normal((nx, ns)) + 0.3).astype(np.float32)     # non-zero mean exercises the mu term
+    time = np.arange(ns) / FS
+    hf = D.gen_template_fincall(time, FS, 17.8, 28.8, 0.68)
+    lf = D.gen_template_fincall(time, FS, 14.7, 21.8, 0.78)
+    assert rel_err(dw.detect.gen_template_fincall(time, FS, 17.8, 28.8, 0.68), hf)[0] == 0
+    outs = dw.detect.compute_cross_correlograms(x, [hf, lf])
+    for o, t in zip(outs, (hf, lf)):
+        ref = D.compute_cross_correlogram(x.astype(np.float64), t)
+        e = rel_err(o, ref)
+        assert e[0] <= 2e-5 and e[1] <= 2e-5, e
+
+
+def test_envelope_and_picks_golden(dw, golden):
+    g = golden("matched_filter")
+    for tag in ("hf", "lf"):
+        env = dw.detect.envelope(g["corr_" + tag])
+        assert rel_err(env, g["env_" + tag])[0] <= 2e-5
+        picks = dw.detect.convert_pick_times(dw.detect.pick_times_env(g["corr_" + tag], 0.05))
+        ref = g["picks_" + tag]
+        # fp32 envelope: allow a pick to move only if it sat exactly at the prominence threshold
+        assert picks.shape[1] >= 1 and abs(picks.shape[1] - ref.shape[1]) <= 1
+        if picks.shape == ref.shape:
+            assert np.array_equal(picks, ref)
+
+
+def test_snr_golden_and_kat(dw, golden):
+    s = golden("snr")
+    out = dw.dsp.snr_tr_array(s["kat_in"])                       # reference KAT tests/test_dsp.py:136-141
+    assert np.allclose(out[0], [-3.01029996, 3.01029996, 6.53212514, 9.03089987, 10.96910013], atol=1e-5)
+    for env in (0, 1):
+        out = dw.dsp.snr_tr_array(s["x"], env=bool(env))
+        ref = s[f"snr_env{env}"]
+        # dB values: compare in the linear domain (10**(dB/10)), relative to the row peak
+        lin, lref = 10 ** (out / 10), 10 ** (ref / 10)
+        assert rel_err(lin, lref)[0] <= TOL, env
+
+
+@pytest.mark.parametrize("ns", [600, 12000, 36000, 120000])
+def test_envelope_vs_oracle_lengths(dw, ns):
+    rng = np.random.default_rng(ns)
+    x = rng.standard_normal((3, ns)).astype(np.float32)
+    env = dw.detect.envelope(x)
+    assert rel_err(env, D.envelope(x.astype(np.float64)))[0] <= 2e-5
+    snr = dw.dsp.snr_tr_array(x, env=True)
+    ref = O.snr_tr_array(x.astype(np.float64), env=True)
+    assert rel_err(10 ** (snr / 10), 10 ** (ref / 10))[0] <= TOL
+
+
+def test_iir_golden(dw, golden):
+    g = golden("iir")
+    x = g["bp_x"]
+    y = dw.dsp.bp_filt(x, FS, 14, 30)
+    e = rel_err(y, g["bp_y"])
+    assert e[0] <= TOL, e
+    sos = dw.dsp.butterworth_filter([5, [10, 30], "bp"], FS)
+    assert rel_err(sos, g["sos_bp5"])[0] <= 1e-14
+    assert rel_err(dw.dsp.sosfiltfilt(sos, x), g["sos_bp5_y"])[0] <= TOL
+    assert rel_err(dw.dsp.sosfiltfilt(g["sos_hp2"], x), g["sos_hp2_y"])[0] <= TOL
+    with pytest.raises(ValueError):      # SciPy: input must be longer than padlen
+        dw.dsp.bp_filt(np.zeros((2, 40)), FS, 14, 30)
+
+
+@pytest.mark.parametrize("nx,ns", [(70, 12000), (33, 5003)])
+def test_bp_filt_vs_oracle(dw, nx, ns):
+    rng = np.random.default_rng(1)
+    x = (rng.standard_normal((nx, ns)) + np.linspace(0, 2, ns)[None, :]).astype(np.float32)   # trend stresses the edges
+    y = dw.dsp.bp_filt(x, FS, 14, 30)
+    ref = O.bp_filt(x.astype(np.float64), FS, 14, 30)
+    e = rel_err(y, ref)
+    assert e[0] <= TOL and e[1] <= TOL, e
+
+
+@pytest.mark.parametrize("nfft,ov", [(128, 0.8), (256, 0.95), (256, 0.9), (160, 0.95)])
+def test_get_spectrogram_vs_oracle(dw, nfft, ov):
+    rng = np.random.default_rng(nfft)
+    y = rng.standard_normal(12000).astype(np.float32)
+    p, tt, ff = dw.dsp.get_spectrogram(y, FS, nfft=nfft, overlap_pct=ov)
+    pr, ttr, ffr = O.get_spectrogram(y.astype(np.float64), FS, nfft=nfft, overlap_pct=ov)
+    assert p.shape == pr.shape and np.allclose(tt, ttr) and np.allclose(ff, ffr)
+    assert rel_err(10 ** (p / 20), 10 ** (pr / 20))[0] <= 2e-5
+
+
+def test_stft_batched(dw):
+    import torch
+    from das4whales_b200 import rows
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((9, 6000)).astype(np.float32)
+    mag = rows.stft_mag(torch.from_numpy(x).cuda(), 160, 8).cpu().numpy()
+    for i in (0, 4, 8):
+        ref = np.abs(O.stft_librosa(x[i].astype(np.float64), 160, 8))
+        assert mag[i].shape == ref.shape
+        assert rel_err(mag[i], ref)[0] <= 2e-5
