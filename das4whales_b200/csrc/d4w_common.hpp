@@ -18,8 +18,10 @@ inline void count_launch(int n = 1) { launch_counter().fetch_add(n, std::memory_
 #define D4W_CUDA_TRY(expr)                                                                          \
     do {                                                                                            \
         cudaError_t e_ = (expr);                                                                    \
-        if (e_ != cudaSuccess)                                                                      \
+        if (e_ != cudaSuccess) {                                                                    \
+            (void)cudaGetLastError(); /* clear the non-sticky error so later CUDA users are not poisoned */ \
             return ::d4w::fail(D4W_ERR_CUDA, std::string(#expr) + " -> " + cudaGetErrorString(e_)); \
+        }                                                                                           \
     } while (0)
 
 #define D4W_CHECK_LAUNCH(name)                                                                      \

@@ -29,6 +29,7 @@ struct d4w_fk_plan {
     float2 *d_tw_col = nullptr, *d_tw_row = nullptr, *d_twT = nullptr;
     int *d_k2pos = nullptr, *d_pos2k = nullptr, *d_pos2k_row = nullptr;
     float* d_taper = nullptr;
+    std::vector<int> h_k2pos;
     int col_threads = 256, row_threads = 256;
     size_t col_smem = 0, row_smem = 0;
 };
@@ -41,6 +42,7 @@ struct d4w_fk_mask {
     int nact = 0;
     std::vector<int> act_k;
     int *d_act_k = nullptr, *d_k2slot = nullptr;
+    int2* d_slot_pos = nullptr;
     float* d_table = nullptr;      // caller-owned
 };
 
@@ -64,7 +66,7 @@ extern "C" int d4w_fk_plan_create(d4w_fk_plan** out, int nx, int ns, int device)
     pl->col.pl = hp.colpl; pl->col.nx = nx; pl->col.ns = ns; pl->col.nc = hp.nc; pl->col.nc_shift = hp.nc_shift;
     pl->col.fstride = hp.fstride; pl->col.aligned = hp.aligned;
     pl->col_smem = hp.col_smem;
-    pl->col_threads = env_int("D4W_COL_THREADS", 256);
+    pl->col_threads = std::min(1024, std::max(32, env_int("D4W_COL_THREADS", 256) / 32 * 32));
     pl->t1 = hp.t1; pl->t2 = hp.t2;
     pl->row.pl = hp.rowpl; pl->row.t1 = hp.t1; pl->row.t2 = hp.t2;
     pl->row_smem = hp.row_smem;
@@ -72,6 +74,7 @@ extern "C" int d4w_fk_plan_create(d4w_fk_plan** out, int nx, int ns, int device)
     const auto &twc = hp.tw_col, &twr = hp.tw_row, &twT = hp.twT;
     const auto &p2k = hp.pos2k, &k2p = hp.k2pos, &p2kr = hp.pos2k_row;
     const auto& tap = hp.taper;
+    pl->h_k2pos = hp.k2pos;
     cudaError_t e = cudaSuccess;
     if (e == cudaSuccess) e = upload(&pl->d_tw_col, twc);
     if (e == cudaSuccess) e = upload(&pl->d_tw_row, twr);
@@ -81,8 +84,12 @@ extern "C" int d4w_fk_plan_create(d4w_fk_plan** out, int nx, int ns, int device)
     if (e == cudaSuccess) e = upload(&pl->d_pos2k_row, p2kr);
     if (e == cudaSuccess) e = upload(&pl->d_taper, tap);
     // the attribute is per-kernel global state: always raise it to the device maximum, never to a plan's own size
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_col_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_col_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_col_fwd<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_col_inv<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_col_fwd<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_col_inv<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_col_fwd<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_col_inv<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_row_mid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
     if (e != cudaSuccess) {
         std::string msg = std::string("d4w_fk_plan_create: ") + cudaGetErrorString(e);
@@ -143,6 +150,12 @@ static int mask_finish_support(d4w_fk_mask* m, void* stream_v) {
     m->nact = (int)m->act_k.size();
     D4W_CUDA_TRY(upload(&m->d_act_k, m->act_k));
     D4W_CUDA_TRY(upload(&m->d_k2slot, k2slot));
+    std::vector<int2> slot_pos((size_t)m->nact);
+    for (int sl = 0; sl < m->nact; ++sl) {
+        const int k = m->act_k[sl];
+        slot_pos[sl] = make_int2(pl->h_k2pos[k], pl->h_k2pos[k == 0 ? 0 : pl->nx - k]);
+    }
+    D4W_CUDA_TRY(upload(&m->d_slot_pos, slot_pos));
     return D4W_OK;
 }
 
@@ -194,7 +207,7 @@ extern "C" int d4w_fk_mask_create_dense(d4w_fk_mask** out, d4w_fk_plan* plan, co
 extern "C" int d4w_fk_mask_destroy(d4w_fk_mask* m) {
     if (!m) return D4W_OK;
     DeviceGuard guard(m->device);
-    cudaFree(m->d_h); cudaFree(m->d_act_k); cudaFree(m->d_k2slot);
+    cudaFree(m->d_h); cudaFree(m->d_act_k); cudaFree(m->d_k2slot); cudaFree(m->d_slot_pos);
     delete m;
     return D4W_OK;
 }
@@ -272,8 +285,15 @@ extern "C" int d4w_fk_apply_pass(d4w_fk_plan* pl, d4w_fk_mask* m, const float* x
         case 1:
             if (!x) return fail(D4W_ERR_ARG, "d4w_fk_apply: null input");
             if (nact == 0) return D4W_OK;
-            k_col_fwd<<<ntiles, pl->col_threads, pl->col_smem, stream>>>(pl->col, x, w, ldw, m->d_act_k, nact,
-                                                                         taper ? pl->d_taper : nullptr);
+            if (pl->col_threads <= 256)
+                k_col_fwd<256><<<ntiles, pl->col_threads, pl->col_smem, stream>>>(pl->col, x, w, ldw, m->d_slot_pos, nact,
+                                                                                  taper ? pl->d_taper : nullptr);
+            else if (pl->col_threads <= 512)
+                k_col_fwd<512><<<ntiles, pl->col_threads, pl->col_smem, stream>>>(pl->col, x, w, ldw, m->d_slot_pos, nact,
+                                                                                  taper ? pl->d_taper : nullptr);
+            else
+                k_col_fwd<1024><<<ntiles, pl->col_threads, pl->col_smem, stream>>>(pl->col, x, w, ldw, m->d_slot_pos, nact,
+                                                                                   taper ? pl->d_taper : nullptr);
             D4W_CHECK_LAUNCH("k_col_fwd");
             return D4W_OK;
         case 2:
@@ -291,7 +311,12 @@ extern "C" int d4w_fk_apply_pass(d4w_fk_plan* pl, d4w_fk_mask* m, const float* x
             return launch_row_split<true>(pl, w, nact, stream);
         case 5:
             if (!y) return fail(D4W_ERR_ARG, "d4w_fk_apply: null output");
-            k_col_inv<<<ntiles, pl->col_threads, pl->col_smem, stream>>>(pl->col, w, ldw, m->d_k2slot, y);
+            if (pl->col_threads <= 256)
+                k_col_inv<256><<<ntiles, pl->col_threads, pl->col_smem, stream>>>(pl->col, w, ldw, m->d_slot_pos, nact, y);
+            else if (pl->col_threads <= 512)
+                k_col_inv<512><<<ntiles, pl->col_threads, pl->col_smem, stream>>>(pl->col, w, ldw, m->d_slot_pos, nact, y);
+            else
+                k_col_inv<1024><<<ntiles, pl->col_threads, pl->col_smem, stream>>>(pl->col, w, ldw, m->d_slot_pos, nact, y);
             D4W_CHECK_LAUNCH("k_col_inv");
             return D4W_OK;
         default:

@@ -91,8 +91,8 @@ extern "C" int d4w_xcorr(d4w_fft_plan* p, const float* x, int nx, int ns, int va
     xp.normalize = normalize ? 1 : 0;
     xp.nseg = (ns + valid - 1) / valid;
     const size_t smem = (size_t)3 * p->n * sizeof(float2);
-    if (smem > p->smem_cap) return fail(D4W_ERR_UNSUPPORTED, "d4w_xcorr: block length too large for shared memory");
-    D4W_CUDA_TRY(cudaFuncSetAttribute(k_xcorr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_cap));
+    if (smem + 1024 > p->smem_cap) return fail(D4W_ERR_UNSUPPORTED, "d4w_xcorr: block length too large for shared memory");
+    D4W_CUDA_TRY(cudaFuncSetAttribute(k_xcorr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_cap - 1024));  // minus its static smem
     dim3 grid((xp.nseg + 1) / 2, nx);
     k_xcorr<<<grid, 256, smem, (cudaStream_t)stream>>>(xp, x, (const float2*)dev_tabs, dev_stats, dev_segpre, dev_mu_over_m, out,
                                                       (size_t)nx * ns);

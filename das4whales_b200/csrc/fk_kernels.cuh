@@ -127,67 +127,114 @@ __host__ __device__ inline void body_mask_build(const MaskParams& mp, float* tab
     tab[idx] = (float)(mask_folded(mp, act_k[slot], f) * scale);
 }
 
+// ------------------------------------------------------------------ async copy helpers
+#ifdef __CUDA_ARCH__
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+#endif
+
 // ------------------------------------------------------------------ P1: column forward (R2C over channels)
+// slot_pos[slot] = (smem position of wavenumber k, position of nx-k) after the forward stages.
 __host__ __device__ inline void body_col_fwd(const ColParams& cp, const float* __restrict__ x, float2* __restrict__ w,
-                                             size_t ldw, const int* __restrict__ act_k, int nact,
+                                             size_t ldw, const int2* __restrict__ slot_pos, int nact,
                                              const float* __restrict__ taper, int bx, int tid, int nthr, float2* smem) {
     const int nc = cp.nc, sh = cp.nc_shift, ns = cp.ns, nx = cp.nx;
     const int t0 = bx * 2 * nc;
-    for (int i = tid; i < (nx << sh); i += nthr) {
-        const int c = i >> sh, col = i & (nc - 1);
-        const int t = t0 + 2 * col;
-        const float* row = x + (size_t)c * ns;
-        float a = 0.f, b = 0.f;
-        if (t + 1 < ns) {
-            if (cp.aligned) { const float2 v = *reinterpret_cast<const float2*>(row + t); a = v.x; b = v.y; }
-            else { a = row[t]; b = row[t + 1]; }
-            if (taper) { a *= taper[t]; b *= taper[t + 1]; }
-        } else if (t < ns) {
-            a = row[t];
-            if (taper) a *= taper[t];
+    bool staged = false;
+#ifdef __CUDA_ARCH__
+    if (cp.aligned && t0 + 2 * nc <= ns) {
+        // whole tile in flight at once: one 8-byte async copy per (channel, column), no register staging
+        for (int i = tid; i < (nx << sh); i += nthr) {
+            const int c = i >> sh, col = i & (nc - 1);
+            cp_async8(smem + col * cp.fstride + c, x + (size_t)c * ns + t0 + 2 * col);
         }
-        smem[col * cp.fstride + c] = make_float2(a, b);
+        cp_async_wait_all();
+        __syncthreads();
+        if (taper) {
+            for (int i = tid; i < (nx << sh); i += nthr) {
+                const int c = i >> sh, col = i & (nc - 1);
+                const int t = t0 + 2 * col;
+                float2 v = smem[col * cp.fstride + c];
+                v.x *= taper[t]; v.y *= taper[t + 1];
+                smem[col * cp.fstride + c] = v;
+            }
+            __syncthreads();
+        }
+        staged = true;
     }
-    D4W_SYNC();
+#endif
+    if (!staged) {
+        for (int i = tid; i < (nx << sh); i += nthr) {
+            const int c = i >> sh, col = i & (nc - 1);
+            const int t = t0 + 2 * col;
+            const float* row = x + (size_t)c * ns;
+            float a = 0.f, b = 0.f;
+            if (t + 1 < ns) {
+                if (cp.aligned) { const float2 v = *reinterpret_cast<const float2*>(row + t); a = v.x; b = v.y; }
+                else { a = row[t]; b = row[t + 1]; }
+                if (taper) { a *= taper[t]; b *= taper[t + 1]; }
+            } else if (t < ns) {
+                a = row[t];
+                if (taper) a *= taper[t];
+            }
+            smem[col * cp.fstride + c] = make_float2(a, b);
+        }
+        D4W_SYNC();
+    }
     fft_forward_stages(smem, cp.pl, cp.tw, nc, cp.fstride, tid, nthr, 0, cp.pl.nstages);
     // two-for-one untangle: column z = x_t + i*x_{t+1}  ->  X_t[k], X_{t+1}[k] for the kept rows
     for (int i = tid; i < (nact << sh); i += nthr) {
         const int slot = i >> sh, col = i & (nc - 1);
-        const int k = act_k[slot];
-        const int p = cp.k2pos[k], p2 = cp.k2pos[k == 0 ? 0 : nx - k];
-        const float2 z = smem[col * cp.fstride + p], z2 = smem[col * cp.fstride + p2];
+        const int2 pp = slot_pos[slot];
+        const float2 z = smem[col * cp.fstride + pp.x], z2 = smem[col * cp.fstride + pp.y];
         const float2 xa = make_float2(0.5f * (z.x + z2.x), 0.5f * (z.y - z2.y));   // (z + conj z2)/2
         const float2 xb = make_float2(0.5f * (z.y + z2.y), 0.5f * (z2.x - z.x));   // (z - conj z2)/(2i)
         const int t = t0 + 2 * col;
         float2* o = w + (size_t)slot * ldw + t;
-        if (t < ns) o[0] = xa;
-        if (t + 1 < ns) o[1] = xb;
+        if (cp.aligned && t + 1 < ns) {
+            *reinterpret_cast<float4*>(o) = make_float4(xa.x, xa.y, xb.x, xb.y);
+        } else {
+            if (t < ns) o[0] = xa;
+            if (t + 1 < ns) o[1] = xb;
+        }
     }
 }
 
 // ------------------------------------------------------------------ P5: column inverse (C2R over channels)
 __host__ __device__ inline void body_col_inv(const ColParams& cp, const float2* __restrict__ w, size_t ldw,
-                                             const int* __restrict__ k2slot, float* __restrict__ y, int bx, int tid,
-                                             int nthr, float2* smem) {
+                                             const int2* __restrict__ slot_pos, int nact, float* __restrict__ y, int bx,
+                                             int tid, int nthr, float2* smem) {
     const int nc = cp.nc, sh = cp.nc_shift, ns = cp.ns, nx = cp.nx;
     const int t0 = bx * 2 * nc;
-    for (int i = tid; i < (nx << sh); i += nthr) {
-        const int p = i >> sh, col = i & (nc - 1);
-        const int k = cp.pos2k[p];
-        const int kk = (2 * k <= nx) ? k : nx - k;
-        const int slot = k2slot[kk];
-        float2 z = make_float2(0.f, 0.f);
-        if (slot >= 0) {
-            const int t = t0 + 2 * col;
-            const float2* src = w + (size_t)slot * ldw + t;
-            float2 y0 = make_float2(0.f, 0.f), y1 = make_float2(0.f, 0.f);
+    // pruned rows are zero: clear the tile, then scatter only the kept rows and their conjugate partners
+    for (int i = tid; i < nc * cp.fstride; i += nthr) smem[i] = make_float2(0.f, 0.f);
+    D4W_SYNC();
+    for (int i = tid; i < (nact << sh); i += nthr) {
+        const int slot = i >> sh, col = i & (nc - 1);
+        const int2 pp = slot_pos[slot];
+        const int t = t0 + 2 * col;
+        const float2* src = w + (size_t)slot * ldw + t;
+        float2 y0 = make_float2(0.f, 0.f), y1 = make_float2(0.f, 0.f);
+        if (cp.aligned && t + 1 < ns) {
+            const float4 v = *reinterpret_cast<const float4*>(src);
+            y0 = make_float2(v.x, v.y); y1 = make_float2(v.z, v.w);
+        } else {
             if (t < ns) y0 = src[0];
             if (t + 1 < ns) y1 = src[1];
-            if (kk == 0 || 2 * kk == nx) { y0.y = 0.f; y1.y = 0.f; }      // self-conjugate rows are real
-            if (k == kk) z = make_float2(y0.x - y1.y, y0.y + y1.x);       // Y_t + i Y_{t+1}
-            else         z = make_float2(y0.x + y1.y, y1.x - y0.y);       // conj(Y_t) + i conj(Y_{t+1})
         }
-        smem[col * cp.fstride + p] = z;
+        if (pp.x == pp.y) {                                   // self-conjugate rows (k = 0, nx/2) are real
+            smem[col * cp.fstride + pp.x] = make_float2(y0.x, y1.x);
+        } else {
+            smem[col * cp.fstride + pp.x] = make_float2(y0.x - y1.y, y0.y + y1.x);   // Y_t + i Y_{t+1}
+            smem[col * cp.fstride + pp.y] = make_float2(y0.x + y1.y, y1.x - y0.y);   // conj(Y_t) + i conj(Y_{t+1})
+        }
     }
     D4W_SYNC();
     fft_inverse_stages(smem, cp.pl, cp.tw, nc, cp.fstride, tid, nthr, 0, cp.pl.nstages);
@@ -246,15 +293,18 @@ __host__ __device__ inline void body_row_mid(const RowParams& rp, float2* __rest
 #ifdef __CUDACC__
 extern __shared__ float2 d4w_dyn_smem[];
 
-static __global__ void __launch_bounds__(256, 1)
-k_col_fwd(ColParams cp, const float* __restrict__ x, float2* __restrict__ w, size_t ldw, const int* __restrict__ act_k,
+template <int MAXT>
+static __global__ void __launch_bounds__(MAXT, 1)
+k_col_fwd(ColParams cp, const float* __restrict__ x, float2* __restrict__ w, size_t ldw, const int2* __restrict__ slot_pos,
           int nact, const float* __restrict__ taper) {
-    body_col_fwd(cp, x, w, ldw, act_k, nact, taper, blockIdx.x, threadIdx.x, blockDim.x, d4w_dyn_smem);
+    body_col_fwd(cp, x, w, ldw, slot_pos, nact, taper, blockIdx.x, threadIdx.x, blockDim.x, d4w_dyn_smem);
 }
 
-static __global__ void __launch_bounds__(256, 1)
-k_col_inv(ColParams cp, const float2* __restrict__ w, size_t ldw, const int* __restrict__ k2slot, float* __restrict__ y) {
-    body_col_inv(cp, w, ldw, k2slot, y, blockIdx.x, threadIdx.x, blockDim.x, d4w_dyn_smem);
+template <int MAXT>
+static __global__ void __launch_bounds__(MAXT, 1)
+k_col_inv(ColParams cp, const float2* __restrict__ w, size_t ldw, const int2* __restrict__ slot_pos, int nact,
+          float* __restrict__ y) {
+    body_col_inv(cp, w, ldw, slot_pos, nact, y, blockIdx.x, threadIdx.x, blockDim.x, d4w_dyn_smem);
 }
 
 template <int T1, bool INV>

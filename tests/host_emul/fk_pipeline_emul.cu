@@ -57,6 +57,8 @@ int main(int argc, char** argv) {
     std::vector<int> act, k2slot(nrows, -1);
     for (int k = 0; k < nrows; ++k) { float v; memcpy(&v, &rowmax[k], 4); if (v > 0.f) { k2slot[k] = (int)act.size(); act.push_back(k); } }
     const int nact = (int)act.size();
+    std::vector<int2> slot_pos(std::max(nact, 1));
+    for (int sl = 0; sl < nact; ++sl) slot_pos[sl] = make_int2(hp.k2pos[act[sl]], hp.k2pos[act[sl] == 0 ? 0 : nx - act[sl]]);
     std::vector<float> tab((size_t)std::max(nact, 1) * ns);
     const double scale = 1.0 / ((double)nx * ns);
     for (size_t i = 0; i < (size_t)nact * ns; ++i) body_mask_build(mp, tab.data(), act.data(), hp.pos2k_row.data(), hp.t1, hp.t2, scale, i);
@@ -67,12 +69,12 @@ int main(int argc, char** argv) {
     const int tile = 2 * hp.nc, ntiles = (ns + tile - 1) / tile;
     if (nact)
         for (int b = 0; b < ntiles; ++b)
-            body_col_fwd(cp, x.data(), w.data(), ldw, act.data(), nact, taper ? hp.taper.data() : nullptr, b, 0, 1, smem.data());
+            body_col_fwd(cp, x.data(), w.data(), ldw, slot_pos.data(), nact, taper ? hp.taper.data() : nullptr, b, 0, 1, smem.data());
     if (hp.t1 > 1 && nact) split_dispatch(hp.t1, false, w.data(), ldw, hp.t2, hp.twT.data(), nact);
     for (int s = 0; s < nact; ++s)
         for (int k1 = 0; k1 < hp.t1; ++k1) body_row_mid(rp, w.data(), ldw, tab.data(), (size_t)ns, k1, s, 0, 1, smem.data());
     if (hp.t1 > 1 && nact) split_dispatch(hp.t1, true, w.data(), ldw, hp.t2, hp.twT.data(), nact);
-    for (int b = 0; b < ntiles; ++b) body_col_inv(cp, w.data(), ldw, k2slot.data(), y.data(), b, 0, 1, smem.data());
+    for (int b = 0; b < ntiles; ++b) body_col_inv(cp, w.data(), ldw, slot_pos.data(), nact, y.data(), b, 0, 1, smem.data());
 
     FILE* fo = fopen(argv[2], "wb");
     fwrite(y.data(), 4, y.size(), fo);
