@@ -65,6 +65,7 @@ extern "C" int d4w_fk_plan_create(d4w_fk_plan** out, int nx, int ns, int device)
     pl->nx = nx; pl->ns = ns; pl->device = device;
     pl->col.pl = hp.colpl; pl->col.nx = nx; pl->col.ns = ns; pl->col.nc = hp.nc; pl->col.nc_shift = hp.nc_shift;
     pl->col.fstride = hp.fstride; pl->col.aligned = hp.aligned;
+    pl->col.dual = hp.dual; pl->col.npair = hp.npair; pl->col.npair_shift = hp.npair_shift; pl->col.aligned16 = hp.aligned16;
     pl->col_smem = hp.col_smem;
     pl->col_threads = std::min(1024, std::max(32, env_int("D4W_COL_THREADS", 256) / 32 * 32));
     pl->t1 = hp.t1; pl->t2 = hp.t2;
@@ -88,6 +89,10 @@ extern "C" int d4w_fk_plan_create(d4w_fk_plan** out, int nx, int ns, int device)
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_col_inv<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_col_fwd<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_col_inv<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_col_fwd_dual<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_col_inv_dual<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_col_fwd_dual<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_col_inv_dual<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_col_fwd<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_col_inv<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_row_mid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
@@ -285,7 +290,13 @@ extern "C" int d4w_fk_apply_pass(d4w_fk_plan* pl, d4w_fk_mask* m, const float* x
         case 1:
             if (!x) return fail(D4W_ERR_ARG, "d4w_fk_apply: null input");
             if (nact == 0) return D4W_OK;
-            if (pl->col_threads <= 256)
+            if (pl->col.dual && pl->col_threads <= 256)
+                k_col_fwd_dual<256><<<ntiles, pl->col_threads, pl->col_smem, stream>>>(pl->col, x, w, ldw, m->d_slot_pos, nact,
+                                                                                       taper ? pl->d_taper : nullptr);
+            else if (pl->col.dual)
+                k_col_fwd_dual<512><<<ntiles, std::min(pl->col_threads, 512), pl->col_smem, stream>>>(
+                    pl->col, x, w, ldw, m->d_slot_pos, nact, taper ? pl->d_taper : nullptr);
+            else if (pl->col_threads <= 256)
                 k_col_fwd<256><<<ntiles, pl->col_threads, pl->col_smem, stream>>>(pl->col, x, w, ldw, m->d_slot_pos, nact,
                                                                                   taper ? pl->d_taper : nullptr);
             else if (pl->col_threads <= 512)
@@ -311,7 +322,12 @@ extern "C" int d4w_fk_apply_pass(d4w_fk_plan* pl, d4w_fk_mask* m, const float* x
             return launch_row_split<true>(pl, w, nact, stream);
         case 5:
             if (!y) return fail(D4W_ERR_ARG, "d4w_fk_apply: null output");
-            if (pl->col_threads <= 256)
+            if (pl->col.dual && pl->col_threads <= 256)
+                k_col_inv_dual<256><<<ntiles, pl->col_threads, pl->col_smem, stream>>>(pl->col, w, ldw, m->d_slot_pos, nact, y);
+            else if (pl->col.dual)
+                k_col_inv_dual<512><<<ntiles, std::min(pl->col_threads, 512), pl->col_smem, stream>>>(pl->col, w, ldw,
+                                                                                                     m->d_slot_pos, nact, y);
+            else if (pl->col_threads <= 256)
                 k_col_inv<256><<<ntiles, pl->col_threads, pl->col_smem, stream>>>(pl->col, w, ldw, m->d_slot_pos, nact, y);
             else if (pl->col_threads <= 512)
                 k_col_inv<512><<<ntiles, pl->col_threads, pl->col_smem, stream>>>(pl->col, w, ldw, m->d_slot_pos, nact, y);

@@ -10,6 +10,7 @@ namespace d4w {
 struct FkHostPlan {
     int nx = 0, ns = 0;
     int t1 = 1, t2 = 0, nc = 1, nc_shift = 0, fstride = 0, aligned = 0;
+    int dual = 0, npair = 0, npair_shift = 0, aligned16 = 0;
     FftPlan colpl{}, rowpl{};
     std::vector<float2> tw_col, tw_row, twT;
     std::vector<int> pos2k, k2pos, pos2k_row;
@@ -50,7 +51,6 @@ inline int build_fk_hostplan(int nx, int ns, size_t smem_cap, FkHostPlan& hp, st
     const int col_maxr = env_int("D4W_COL_MAX_RADIX", 25);
     const int row_maxr = env_int("D4W_ROW_MAX_RADIX", 16);
     std::string e2;
-    if (!make_plan(nx, col_maxr, hp.colpl, e2)) { err = "channel axis: " + e2; return 1; }
     int nc = 8;
     const size_t col_budget = std::min<size_t>(smem_cap, 200 * 1024);
     while (nc > 1 && (size_t)nc * (nx + 1) * sizeof(float2) > col_budget) nc >>= 1;
@@ -66,6 +66,12 @@ inline int build_fk_hostplan(int nx, int ns, size_t smem_cap, FkHostPlan& hp, st
     hp.fstride = nx | 1;
     hp.aligned = (ns % 2 == 0) ? 1 : 0;
     hp.col_smem = (size_t)nc * hp.fstride * sizeof(float2);
+    // dual-lane (f32x2) column kernels: two complex columns per thread, radix <= 16 (register budget)
+    hp.dual = (nc >= 2 && env_int("D4W_COL_DUAL", 1)) ? 1 : 0;
+    hp.npair = nc / 2;
+    hp.npair_shift = (hp.npair <= 1) ? 0 : (hp.npair == 2) ? 1 : 2;
+    hp.aligned16 = (ns % 4 == 0) ? 1 : 0;
+    if (!make_plan(nx, hp.dual ? std::min(col_maxr, 16) : col_maxr, hp.colpl, e2)) { err = "channel axis: " + e2; return 1; }
 
     int t1 = 0;
     const int forced_t1 = env_int("D4W_T1", 0);

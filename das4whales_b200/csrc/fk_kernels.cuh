@@ -16,6 +16,7 @@
 // same code on the CPU with nthr = 1.
 #pragma once
 #include "fft_smem.cuh"
+#include "fft_dual.cuh"
 
 namespace d4w {
 
@@ -29,6 +30,9 @@ struct ColParams {
     int nc_shift;          // log2(nc)
     int fstride;           // smem stride between columns (float2 units)
     int aligned;           // rows 8-byte aligned (ns even) -> float2 global accesses
+    int dual;              // 1: dual-lane (f32x2) kernels, tile = 4*npair samples stored as cpd elements
+    int npair, npair_shift;
+    int aligned16;         // rows 16-byte aligned (ns % 4 == 0)
 };
 
 struct RowParams {
@@ -252,6 +256,129 @@ __host__ __device__ inline void body_col_inv(const ColParams& cp, const float2* 
     }
 }
 
+
+// ================================================================== dual-lane column passes (f32x2)
+// Tile = 4*npair time samples.  Pair pr of channel c holds samples t = t0 + 4*pr + {0,1,2,3} as the
+// 16-byte element {a0, a1, a2, a3} = cpd{x = (a0, a1), y = (a2, a3)}: lane A is the complex column
+// a0 + i*a2 (samples t, t+2), lane B is a1 + i*a3 (samples t+1, t+3) -- exactly the memory image of
+// the row, so the load is one 16-byte cp.async and the store one 16-byte st per channel.
+__host__ __device__ inline void body_col_fwd_dual(const ColParams& cp, const float* __restrict__ x, float2* __restrict__ w,
+                                                  size_t ldw, const int2* __restrict__ slot_pos, int nact,
+                                                  const float* __restrict__ taper, int bx, int tid, int nthr, cpd* smem) {
+    const int np = cp.npair, sh = cp.npair_shift, ns = cp.ns, nx = cp.nx;
+    const int t0 = bx * 4 * np;
+    bool staged = false;
+#ifdef __CUDA_ARCH__
+    if (cp.aligned16 && t0 + 4 * np <= ns) {
+        for (int i = tid; i < (nx << sh); i += nthr) {
+            const int c = i >> sh, pr = i & (np - 1);
+            cp_async16(smem + pr * cp.fstride + c, x + (size_t)c * ns + t0 + 4 * pr);
+        }
+        cp_async_wait_all();
+        __syncthreads();
+        if (taper) {
+            for (int i = tid; i < (nx << sh); i += nthr) {
+                const int c = i >> sh, pr = i & (np - 1);
+                const int t = t0 + 4 * pr;
+                cpd v = smem[pr * cp.fstride + c];
+                v.x = vmul(v.x, f2x_set(taper[t], taper[t + 1]));
+                v.y = vmul(v.y, f2x_set(taper[t + 2], taper[t + 3]));
+                smem[pr * cp.fstride + c] = v;
+            }
+            __syncthreads();
+        }
+        staged = true;
+    }
+#endif
+    if (!staged) {
+        for (int i = tid; i < (nx << sh); i += nthr) {
+            const int c = i >> sh, pr = i & (np - 1);
+            const int t = t0 + 4 * pr;
+            const float* row = x + (size_t)c * ns;
+            float a[4];
+            for (int q = 0; q < 4; ++q) {
+                a[q] = (t + q < ns) ? row[t + q] : 0.f;
+                if (taper && t + q < ns) a[q] *= taper[t + q];
+            }
+            smem[pr * cp.fstride + c] = dmake(f2x_set(a[0], a[1]), f2x_set(a[2], a[3]));
+        }
+        D4W_SYNC();
+    }
+    fft_forward_stages_dual(smem, cp.pl, cp.tw, np, cp.fstride, tid, nthr);
+    const f2x half = vbc(0.5f);
+    for (int i = tid; i < (nact << sh); i += nthr) {
+        const int slot = i >> sh, pr = i & (np - 1);
+        const int2 pp = slot_pos[slot];
+        const cpd z = smem[pr * cp.fstride + pp.x], z2 = smem[pr * cp.fstride + pp.y];
+        // lane-wise two-for-one untangle: Xa = (z + conj z2)/2, Xb = (z - conj z2)/(2i)
+        const cpd xa = dmake(vmul(vadd(z.x, z2.x), half), vmul(vsub(z.y, z2.y), half));
+        const cpd xb = dmake(vmul(vadd(z.y, z2.y), half), vmul(vsub(z2.x, z.x), half));
+        const int t = t0 + 4 * pr;
+        float2* o = w + (size_t)slot * ldw + t;
+        // lane A of xa -> sample t, lane B of xa -> t+1, lane A of xb -> t+2, lane B of xb -> t+3
+        const float2 o0 = make_float2(f2x_lo(xa.x), f2x_lo(xa.y)), o1 = make_float2(f2x_hi(xa.x), f2x_hi(xa.y));
+        const float2 o2 = make_float2(f2x_lo(xb.x), f2x_lo(xb.y)), o3 = make_float2(f2x_hi(xb.x), f2x_hi(xb.y));
+        if (cp.aligned16 && t + 3 < ns) {
+            reinterpret_cast<float4*>(o)[0] = make_float4(o0.x, o0.y, o1.x, o1.y);
+            reinterpret_cast<float4*>(o)[1] = make_float4(o2.x, o2.y, o3.x, o3.y);
+        } else {
+            if (t < ns) o[0] = o0;
+            if (t + 1 < ns) o[1] = o1;
+            if (t + 2 < ns) o[2] = o2;
+            if (t + 3 < ns) o[3] = o3;
+        }
+    }
+}
+
+__host__ __device__ inline void body_col_inv_dual(const ColParams& cp, const float2* __restrict__ w, size_t ldw,
+                                                  const int2* __restrict__ slot_pos, int nact, float* __restrict__ y, int bx,
+                                                  int tid, int nthr, cpd* smem) {
+    const int np = cp.npair, sh = cp.npair_shift, ns = cp.ns, nx = cp.nx;
+    const int t0 = bx * 4 * np;
+    const cpd zero = dmake(vbc(0.f), vbc(0.f));
+    for (int i = tid; i < np * cp.fstride; i += nthr) smem[i] = zero;
+    D4W_SYNC();
+    for (int i = tid; i < (nact << sh); i += nthr) {
+        const int slot = i >> sh, pr = i & (np - 1);
+        const int2 pp = slot_pos[slot];
+        const int t = t0 + 4 * pr;
+        const float2* src = w + (size_t)slot * ldw + t;
+        float2 y0 = make_float2(0.f, 0.f), y1 = y0, y2 = y0, y3 = y0;
+        if (cp.aligned16 && t + 3 < ns) {
+            const float4 u = reinterpret_cast<const float4*>(src)[0], v = reinterpret_cast<const float4*>(src)[1];
+            y0 = make_float2(u.x, u.y); y1 = make_float2(u.z, u.w); y2 = make_float2(v.x, v.y); y3 = make_float2(v.z, v.w);
+        } else {
+            if (t < ns) y0 = src[0];
+            if (t + 1 < ns) y1 = src[1];
+            if (t + 2 < ns) y2 = src[2];
+            if (t + 3 < ns) y3 = src[3];
+        }
+        // lane A: Y_t + i Y_{t+2};  lane B: Y_{t+1} + i Y_{t+3}
+        if (pp.x == pp.y) {                                   // self-conjugate rows are real
+            smem[pr * cp.fstride + pp.x] = dmake(f2x_set(y0.x, y1.x), f2x_set(y2.x, y3.x));
+        } else {
+            smem[pr * cp.fstride + pp.x] = dmake(f2x_set(y0.x - y2.y, y1.x - y3.y), f2x_set(y0.y + y2.x, y1.y + y3.x));
+            smem[pr * cp.fstride + pp.y] = dmake(f2x_set(y0.x + y2.y, y1.x + y3.y), f2x_set(y2.x - y0.y, y3.x - y1.y));
+        }
+    }
+    D4W_SYNC();
+    fft_inverse_stages_dual(smem, cp.pl, cp.tw, np, cp.fstride, tid, nthr);
+    for (int i = tid; i < (nx << sh); i += nthr) {
+        const int c = i >> sh, pr = i & (np - 1);
+        const cpd z = smem[pr * cp.fstride + c];
+        const int t = t0 + 4 * pr;
+        float* row = y + (size_t)c * ns + t;
+        if (cp.aligned16 && t + 3 < ns) {
+            *reinterpret_cast<float4*>(row) = make_float4(f2x_lo(z.x), f2x_hi(z.x), f2x_lo(z.y), f2x_hi(z.y));
+        } else {
+            if (t < ns) row[0] = f2x_lo(z.x);
+            if (t + 1 < ns) row[1] = f2x_hi(z.x);
+            if (t + 2 < ns) row[2] = f2x_lo(z.y);
+            if (t + 3 < ns) row[3] = f2x_hi(z.y);
+        }
+    }
+}
+
 // ------------------------------------------------------------------ P2 / P4: radix-T1 time split (registers only)
 template <int T1, bool INV>
 __host__ __device__ inline void body_row_split(float2* __restrict__ w, size_t ldw, int t2len, const float2* __restrict__ twT,
@@ -291,7 +418,7 @@ __host__ __device__ inline void body_row_mid(const RowParams& rp, float2* __rest
 
 // ================================================================== __global__ wrappers
 #ifdef __CUDACC__
-extern __shared__ float2 d4w_dyn_smem[];
+extern __shared__ __align__(16) float2 d4w_dyn_smem[];
 
 template <int MAXT>
 static __global__ void __launch_bounds__(MAXT, 1)
@@ -305,6 +432,20 @@ static __global__ void __launch_bounds__(MAXT, 1)
 k_col_inv(ColParams cp, const float2* __restrict__ w, size_t ldw, const int2* __restrict__ slot_pos, int nact,
           float* __restrict__ y) {
     body_col_inv(cp, w, ldw, slot_pos, nact, y, blockIdx.x, threadIdx.x, blockDim.x, d4w_dyn_smem);
+}
+
+template <int MAXT>
+static __global__ void __launch_bounds__(MAXT, 1)
+k_col_fwd_dual(ColParams cp, const float* __restrict__ x, float2* __restrict__ w, size_t ldw, const int2* __restrict__ slot_pos,
+               int nact, const float* __restrict__ taper) {
+    body_col_fwd_dual(cp, x, w, ldw, slot_pos, nact, taper, blockIdx.x, threadIdx.x, blockDim.x, reinterpret_cast<cpd*>(d4w_dyn_smem));
+}
+
+template <int MAXT>
+static __global__ void __launch_bounds__(MAXT, 1)
+k_col_inv_dual(ColParams cp, const float2* __restrict__ w, size_t ldw, const int2* __restrict__ slot_pos, int nact,
+               float* __restrict__ y) {
+    body_col_inv_dual(cp, w, ldw, slot_pos, nact, y, blockIdx.x, threadIdx.x, blockDim.x, reinterpret_cast<cpd*>(d4w_dyn_smem));
 }
 
 template <int T1, bool INV>

@@ -37,12 +37,13 @@ if "--one" in sys.argv:
     sys.exit(0)
 
 configs = []
-for thr, maxr in itertools.product((256, 512, 1024), (25, 16, 10)):
+for thr, maxr in itertools.product((256, 512), (16, 10, 8)):
     configs.append({"D4W_COL_THREADS": thr, "D4W_COL_MAX_RADIX": maxr})
+configs.append({"D4W_COL_DUAL": 0, "D4W_COL_THREADS": 512})
 for t1, rthr, rmaxr in ((12, 256, 16), (12, 512, 16), (12, 256, 10), (24, 256, 16), (25, 256, 16), (20, 256, 16), (15, 256, 16), (12, 256, 25)):
     configs.append({"D4W_T1": t1, "D4W_ROW_THREADS": rthr, "D4W_ROW_MAX_RADIX": rmaxr})
 if len(sys.argv) > 1 and sys.argv[1] == "--col":
-    configs = configs[:9]
+    configs = configs[:7]
 for cfg in configs:
     env = dict(os.environ)
     env.update({k: str(v) for k, v in cfg.items()})

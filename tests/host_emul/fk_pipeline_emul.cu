@@ -45,6 +45,7 @@ int main(int argc, char** argv) {
     if (build_fk_hostplan(nx, ns, 227 * 1024, hp, err)) { fprintf(stderr, "plan: %s\n", err.c_str()); return 4; }
     ColParams cp{}; cp.pl = hp.colpl; cp.tw = hp.tw_col.data(); cp.k2pos = hp.k2pos.data(); cp.pos2k = hp.pos2k.data();
     cp.nx = nx; cp.ns = ns; cp.nc = hp.nc; cp.nc_shift = hp.nc_shift; cp.fstride = hp.fstride; cp.aligned = hp.aligned;
+    cp.dual = hp.dual; cp.npair = hp.npair; cp.npair_shift = hp.npair_shift; cp.aligned16 = hp.aligned16;
     RowParams rp{}; rp.pl = hp.rowpl; rp.tw = hp.tw_row.data(); rp.twT = hp.twT.data(); rp.t1 = hp.t1; rp.t2 = hp.t2;
     MaskParams mp{}; mp.kind = kind; mp.nx = nx; mp.ns = ns; mp.kval = par[0]; mp.fval = par[1];
     mp.c0 = par[2]; mp.c1 = par[3]; mp.c2 = par[4]; mp.c3 = par[5];
@@ -68,18 +69,23 @@ int main(int argc, char** argv) {
     const size_t ldw = ns;
     const int tile = 2 * hp.nc, ntiles = (ns + tile - 1) / tile;
     if (nact)
-        for (int b = 0; b < ntiles; ++b)
-            body_col_fwd(cp, x.data(), w.data(), ldw, slot_pos.data(), nact, taper ? hp.taper.data() : nullptr, b, 0, 1, smem.data());
+        for (int b = 0; b < ntiles; ++b) {
+            if (hp.dual) body_col_fwd_dual(cp, x.data(), w.data(), ldw, slot_pos.data(), nact, taper ? hp.taper.data() : nullptr, b, 0, 1, reinterpret_cast<cpd*>(smem.data()));
+            else body_col_fwd(cp, x.data(), w.data(), ldw, slot_pos.data(), nact, taper ? hp.taper.data() : nullptr, b, 0, 1, smem.data());
+        }
     if (hp.t1 > 1 && nact) split_dispatch(hp.t1, false, w.data(), ldw, hp.t2, hp.twT.data(), nact);
     for (int s = 0; s < nact; ++s)
         for (int k1 = 0; k1 < hp.t1; ++k1) body_row_mid(rp, w.data(), ldw, tab.data(), (size_t)ns, k1, s, 0, 1, smem.data());
     if (hp.t1 > 1 && nact) split_dispatch(hp.t1, true, w.data(), ldw, hp.t2, hp.twT.data(), nact);
-    for (int b = 0; b < ntiles; ++b) body_col_inv(cp, w.data(), ldw, slot_pos.data(), nact, y.data(), b, 0, 1, smem.data());
+    for (int b = 0; b < ntiles; ++b) {
+        if (hp.dual) body_col_inv_dual(cp, w.data(), ldw, slot_pos.data(), nact, y.data(), b, 0, 1, reinterpret_cast<cpd*>(smem.data()));
+        else body_col_inv(cp, w.data(), ldw, slot_pos.data(), nact, y.data(), b, 0, 1, smem.data());
+    }
 
     FILE* fo = fopen(argv[2], "wb");
     fwrite(y.data(), 4, y.size(), fo);
     fwrite(&nact, 4, 1, fo);
-    int info[4] = {hp.t1, hp.t2, hp.nc, hp.colpl.nstages};
+    int info[4] = {hp.t1, hp.t2, hp.nc, hp.dual ? 100 + hp.colpl.nstages : hp.colpl.nstages};
     fwrite(info, 4, 4, fo);
     fclose(fo);
     return 0;
