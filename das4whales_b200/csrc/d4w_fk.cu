@@ -67,7 +67,7 @@ extern "C" int d4w_fk_plan_create(d4w_fk_plan** out, int nx, int ns, int device)
     pl->col.fstride = hp.fstride; pl->col.aligned = hp.aligned;
     pl->col.dual = hp.dual; pl->col.npair = hp.npair; pl->col.npair_shift = hp.npair_shift; pl->col.aligned16 = hp.aligned16;
     pl->col_smem = hp.col_smem;
-    pl->col_threads = std::min(1024, std::max(32, env_int("D4W_COL_THREADS", 256) / 32 * 32));
+    pl->col_threads = std::min(1024, std::max(32, env_int("D4W_COL_THREADS", 512) / 32 * 32));
     pl->t1 = hp.t1; pl->t2 = hp.t2;
     pl->row.pl = hp.rowpl; pl->row.t1 = hp.t1; pl->row.t2 = hp.t2;
     pl->row_smem = hp.row_smem;

@@ -216,14 +216,15 @@ extern "C" int d4w_sosfiltfilt(const float* x, float* y, float* tmp, int nx, int
 
 // ------------------------------------------------------------------ batched STFT magnitude
 extern "C" int d4w_stft_mag(d4w_fft_plan* p, const float* x, float* out, int nx, int ns, int hop, const float* dev_window,
-                            void* stream_v) {
+                            int bin_lo, int bin_hi, void* stream_v) {
     if (!p || !x || !out || !dev_window) return fail(D4W_ERR_ARG, "d4w_stft_mag: null argument");
     if (p->n % 2 || hop < 1) return fail(D4W_ERR_ARG, "d4w_stft_mag: n_fft must be even and hop >= 1");
     if (nx > 65535) return fail(D4W_ERR_UNSUPPORTED, "d4w_stft_mag: more than 65535 rows per call");
     DeviceGuard guard(p->device);
     StftParams sp{};
     sp.pl = p->pl; sp.tw = p->d_tw; sp.k2pos = p->d_k2pos;
-    sp.nfft = p->n; sp.hop = hop; sp.ns = ns; sp.nframes = 1 + ns / hop; sp.nbins = p->n / 2 + 1;
+    if (bin_lo < 0 || bin_hi > p->n / 2 || bin_lo > bin_hi) return fail(D4W_ERR_ARG, "d4w_stft_mag: bad bin range");
+    sp.nfft = p->n; sp.hop = hop; sp.ns = ns; sp.nframes = 1 + ns / hop; sp.nbins = bin_hi - bin_lo + 1; sp.bin_lo = bin_lo;
     int fpb = 32;
     while (fpb > 2 && (size_t)(fpb / 2) * (p->n + 1) * sizeof(float2) > 96 * 1024) fpb >>= 1;
     sp.fpb = fpb;
@@ -233,5 +234,34 @@ extern "C" int d4w_stft_mag(d4w_fft_plan* p, const float* x, float* out, int nx,
     dim3 grid((sp.nframes + fpb - 1) / fpb, nx);
     k_stft_mag<<<grid, 256, smem, (cudaStream_t)stream_v>>>(sp, x, dev_window, out);
     D4W_CHECK_LAUNCH("k_stft_mag");
+    return D4W_OK;
+}
+
+// ------------------------------------------------------------------ medians / maxima / spectrogram correlation
+extern "C" int d4w_row_median(const float* x, int nrows, size_t n, float* med, void* stream) {
+    if (!x || !med || nrows < 1 || n < 1) return fail(D4W_ERR_ARG, "d4w_row_median: bad argument");
+    k_row_median<<<nrows, 512, 0, (cudaStream_t)stream>>>(x, n, med);
+    D4W_CHECK_LAUNCH("k_row_median");
+    return D4W_OK;
+}
+
+extern "C" int d4w_row_max(const float* x, int nrows, size_t n, float* mx, void* stream) {
+    if (!x || !mx || nrows < 1 || n < 1) return fail(D4W_ERR_ARG, "d4w_row_max: bad argument");
+    k_row_max<<<nrows, 256, 0, (cudaStream_t)stream>>>(x, n, mx);
+    D4W_CHECK_LAUNCH("k_row_max");
+    return D4W_OK;
+}
+
+extern "C" int d4w_speccorr(const float* S, int nx, int nf, int nt, const float* K, int kw, const float* med, float* out,
+                            void* stream) {
+    if (!S || !K || !med || !out || nx < 1 || nf < 1 || nt < 1 || kw < 1) return fail(D4W_ERR_ARG, "d4w_speccorr: bad argument");
+    if (nx > 65535) return fail(D4W_ERR_UNSUPPORTED, "d4w_speccorr: more than 65535 rows per call");
+    const int tile = 256;
+    const size_t smem = ((size_t)nf * kw + (size_t)nf * (tile + kw)) * sizeof(float);
+    if (smem > 200 * 1024) return fail(D4W_ERR_UNSUPPORTED, "d4w_speccorr: kernel too large for shared memory");
+    D4W_CUDA_TRY(cudaFuncSetAttribute(k_speccorr, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    dim3 grid((nt + tile - 1) / tile, nx);
+    k_speccorr<<<grid, tile, smem, (cudaStream_t)stream>>>(S, nf, nt, K, kw, med, out);
+    D4W_CHECK_LAUNCH("k_speccorr");
     return D4W_OK;
 }

@@ -321,7 +321,8 @@ struct StftParams {
     FftPlan pl;
     const float2* tw;
     const int* k2pos;
-    int nfft, hop, ns, nframes, nbins, fpb;      // fpb = frames per block (even)
+    int nfft, hop, ns, nframes, nbins, fpb;      // fpb = frames per block (even); nbins = bins written
+    int bin_lo;                                  // first DFT bin written (band slice of detect.py:390-392)
 };
 
 static __global__ void __launch_bounds__(256)
@@ -346,7 +347,8 @@ k_stft_mag(StftParams sp, const float* __restrict__ x, const float* __restrict__
     fft_forward_stages(sm, sp.pl, sp.tw, npair, fstride, tid, nthr, 0, sp.pl.nstages);
     float* o = out + row * (size_t)sp.nbins * sp.nframes;
     for (int i = tid; i < sp.nbins * sp.fpb; i += nthr) {
-        const int k = i / sp.fpb, f = i - k * sp.fpb;          // frame fastest -> contiguous stores
+        const int kk = i / sp.fpb, f = i - kk * sp.fpb;        // frame fastest -> contiguous stores
+        const int k = kk + sp.bin_lo;
         const int m = m0 + f;
         if (m >= sp.nframes) continue;
         const int q = f >> 1;
@@ -355,8 +357,99 @@ k_stft_mag(StftParams sp, const float* __restrict__ x, const float* __restrict__
         float2 v;
         if ((f & 1) == 0) v = make_float2(0.5f * (z.x + z2.x), 0.5f * (z.y - z2.y));
         else              v = make_float2(0.5f * (z.y + z2.y), 0.5f * (z2.x - z.x));
-        o[(size_t)k * sp.nframes + m] = sqrtf(v.x * v.x + v.y * v.y);
+        o[(size_t)kk * sp.nframes + m] = sqrtf(v.x * v.x + v.y * v.y);
     }
+}
+
+
+// ------------------------------------------------------------------ per-row median of non-negative floats
+// np.median over each row (detect.xcorr2d divides by median(spectro), detect.py:600).  Exact
+// 3-pass radix select on the float bit patterns (monotone for x >= 0): 11 + 11 + 10 bits, the
+// row is re-read from L2 each pass.  Even counts average the two middle order statistics.
+__device__ __forceinline__ unsigned int select_rank(const float* __restrict__ r, size_t n, size_t rank, unsigned int* hist) {
+    unsigned int prefix = 0, mask = 0;
+    const int shifts[3] = {21, 10, 0};
+    const int bits[3] = {11, 11, 10};
+    for (int pass = 0; pass < 3; ++pass) {
+        const int nb = 1 << bits[pass];
+        for (int i = threadIdx.x; i < nb; i += blockDim.x) hist[i] = 0;
+        __syncthreads();
+        for (size_t i = threadIdx.x; i < n; i += blockDim.x) {
+            const unsigned int u = __float_as_uint(r[i]);
+            if ((u & mask) == prefix) atomicAdd(&hist[(u >> shifts[pass]) & (nb - 1)], 1u);
+        }
+        __syncthreads();
+        __shared__ unsigned int s_bin;
+        __shared__ unsigned long long s_rank;
+        if (threadIdx.x == 0) {
+            unsigned long long acc = 0;
+            int b = 0;
+            for (; b < nb; ++b) { if (acc + hist[b] > rank) break; acc += hist[b]; }
+            s_bin = (unsigned int)b; s_rank = rank - acc;
+        }
+        __syncthreads();
+        prefix |= s_bin << shifts[pass];
+        mask |= (unsigned int)(nb - 1) << shifts[pass];
+        rank = (size_t)s_rank;
+        __syncthreads();
+    }
+    return prefix;
+}
+
+static __global__ void __launch_bounds__(512)
+k_row_median(const float* __restrict__ x, size_t n, float* __restrict__ med) {
+    __shared__ unsigned int hist[2048];
+    const float* r = x + (size_t)blockIdx.x * n;
+    const float hi = __uint_as_float(select_rank(r, n, n / 2, hist));
+    float lo = hi;
+    if ((n & 1) == 0) lo = __uint_as_float(select_rank(r, n, n / 2 - 1, hist));
+    if (threadIdx.x == 0) med[blockIdx.x] = 0.5f * (lo + hi);
+}
+
+// ------------------------------------------------------------------ spectrogram x kernel correlation (detect.xcorr2d)
+// out[row][t] = max(0, sum_f sum_j S[row][f][t - c0 + j] * K[f][j]) / (median[row] * kw),  c0 = ceil((kw-1)/2)
+// = fftconvolve(S, flip(K, axis=1), 'same', axes=1).sum(0), clipped and normalised (detect.py:597-600).
+static __global__ void __launch_bounds__(256)
+k_speccorr(const float* __restrict__ S, int nf, int nt, const float* __restrict__ K, int kw, const float* __restrict__ med,
+           float* __restrict__ out) {
+    extern __shared__ float sh[];
+    float* sk = sh;                          // [nf][kw]
+    float* st = sh + nf * kw;                // [nf][tile + kw]
+    const int tile = blockDim.x, w = tile + kw;
+    const size_t row = blockIdx.y;
+    const int t0 = blockIdx.x * tile;
+    const int c0 = kw / 2;                   // ceil((kw-1)/2)
+    for (int i = threadIdx.x; i < nf * kw; i += blockDim.x) sk[i] = K[i];
+    const float* Sr = S + row * (size_t)nf * nt;
+    for (int i = threadIdx.x; i < nf * w; i += blockDim.x) {
+        const int f = i / w, j = i - f * w;
+        const int t = t0 - c0 + j;
+        st[i] = (t >= 0 && t < nt) ? Sr[(size_t)f * nt + t] : 0.f;
+    }
+    __syncthreads();
+    const int t = t0 + threadIdx.x;
+    if (t >= nt) return;
+    float acc = 0.f;
+    for (int f = 0; f < nf; ++f) {
+        const float* a = st + f * w + threadIdx.x;
+        const float* b = sk + f * kw;
+        for (int j = 0; j < kw; ++j) acc = fmaf(a[j], b[j], acc);
+    }
+    acc = fmaxf(acc, 0.f);
+    out[row * nt + t] = acc / (med[row] * (float)kw);
+}
+
+// per-row maximum (spectrogram normalisation max(S) of dsp.py:76 / detect.py:387)
+static __global__ void __launch_bounds__(256)
+k_row_max(const float* __restrict__ x, size_t n, float* __restrict__ mx) {
+    __shared__ float s[8];
+    const float* r = x + (size_t)blockIdx.x * n;
+    float m = 0.f;
+    for (size_t i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, r[i]);
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) { for (int w = 1; w < 8; ++w) m = fmaxf(m, s[w]); mx[blockIdx.x] = fmaxf(m, s[0]); }
 }
 
 }  // namespace d4w

@@ -100,3 +100,89 @@ def select_picked_times(idx_tp, tstart, tend, fs):
 # north-star aliases
 matched_filter = compute_cross_correlogram
 xcorr_templates = compute_cross_correlograms
+
+
+# ---- spectrogram-correlation detector (reference: detect.py:334-708) -----------------------
+def _band_bins(nfft, fs, fmin, fmax):
+    ff = np.linspace(0, fs / 2, num=nfft // 2 + 1)
+    sel = np.where((ff >= fmin) & (ff <= fmax))[0]
+    if len(sel) == 0:
+        raise ValueError("no STFT bin inside [fmin, fmax]")
+    return ff, int(sel[0]), int(sel[-1])
+
+
+def get_sliced_nspectrogram(trace, fs, fmin, fmax, nperseg, nhop, plotflag=False):
+    """|STFT| / max, rows with fmin <= f <= fmax (reference: detect.py:334-408)."""
+    import torch
+    xd = _to_device(np.asarray(trace)[None, :] if not _is_tensor(trace) else trace.reshape(1, -1))
+    ff, b0, b1 = _band_bins(nperseg, fs, fmin, fmax)
+    full = _rows.stft_mag(xd, nperseg, nhop)                       # max is taken over ALL bins (detect.py:387)
+    mx = _rows.row_max(full.reshape(1, -1))
+    p = full[0, b0:b1 + 1] / mx
+    nt = p.shape[1]
+    tt = np.linspace(0, xd.shape[1] / fs, num=nt)
+    if plotflag:
+        import matplotlib.pyplot as plt
+        plt.pcolormesh(tt, ff[b0:b1 + 1], 20 * np.log10(p.cpu().numpy() / float(p.max())))
+        plt.show()
+    return (p if _is_tensor(trace) else p.to(torch.float64).cpu().numpy()), ff[b0:b1 + 1], tt
+
+
+def buildkernel(f0, f1, bdwdth, dur, f, t, samp, fmin, fmax, plotflag=False):
+    """Hat-function hyperbolic-sweep kernel x Hann in time (reference: detect.py:411-492).
+    Host side: the kernel is a few hundred values."""
+    tvec = np.linspace(0, dur, np.size(np.nonzero((t < dur * 8) & (t > dur * 7))))
+    fvec = np.asarray(f)
+    x = fvec[:, None] - (f0 * f1 * dur / ((f0 - f1) * tvec[None, :] + f1 * dur))
+    kdist = (1 - np.square(x) / (bdwdth * bdwdth)) * np.exp(-np.square(x) / (2 * (bdwdth * bdwdth)))
+    return tvec, fvec, kdist * np.hanning(len(tvec))[np.newaxis, :]
+
+
+def buildkernel_from_template(fmin, fmax, dur, fs, nperseg, nhop, plotflag=False):
+    """Spectrogram of the windowed template as a kernel (reference: detect.py:495-541)."""
+    template = gen_hyperbolic_chirp(fmin, fmax, dur, fs)
+    template *= np.hanning(len(template))
+    spectro, _, _ = get_sliced_nspectrogram(template, fs, fmin, fmax, nperseg, nhop, plotflag=False)
+    return spectro
+
+
+def xcorr2d(spectro, kernel):
+    """Sum over frequency of the time-correlation of spectrogram and kernel, clipped at zero and
+    divided by median(spectro) * kernel width (reference: detect.py:579-602)."""
+    import torch
+    if _is_tensor(spectro):
+        S = spectro.to(torch.float32).contiguous()[None]
+    else:
+        S = torch.from_numpy(np.ascontiguousarray(spectro, dtype=np.float32)).cuda()[None]
+    out = _rows.spectro_correlate(S, kernel)[0]
+    return out if _is_tensor(spectro) else out.to(torch.float64).cpu().numpy()
+
+
+def compute_cross_correlogram_spectrocorr(data, fs, flims, kernel, win_size, overlap_pct):
+    """Spectrogram-correlation detector over all channels (reference: detect.py:650-708): batched
+    STFT of the band of interest, kernel correlation + frequency sum, median normalisation, all
+    on the GPU in channel chunks."""
+    import torch
+    nperseg = int(win_size * fs)
+    nhop = int(np.floor(nperseg * (1 - overlap_pct)))
+    noverlap = nperseg - nhop
+    print(f'nperseg: {nperseg}, noverlap: {noverlap}, hop_length: {nhop}')
+    fmin, fmax = flims
+    f1, f0, duration, bandwidth = kernel["f1"], kernel["f0"], kernel["dur"], kernel["bdwidth"]
+    if fmax - f1 < 2 * bandwidth:
+        fmax = f1 + 3 * bandwidth
+    if f0 - fmin < 2 * bandwidth:
+        fmin = f0 - 3 * bandwidth
+    xd = _to_device(data)
+    nx, ns = xd.shape
+    ff, b0, b1 = _band_bins(nperseg, fs, fmin, fmax)
+    nt = 1 + ns // nhop
+    tt = np.linspace(0, ns / fs, num=nt)
+    _, _, ker = buildkernel(f0, f1, bandwidth, duration, ff[b0:b1 + 1], tt, fs, fmin, fmax, plotflag=False)
+    out = torch.empty((nx, nt), dtype=torch.float32, device=xd.device)
+    nf = b1 - b0 + 1
+    chunk = max(1, min(nx, (2 << 30) // max(1, nf * nt * 4)))
+    for r0 in range(0, nx, chunk):
+        S = _rows.stft_mag(xd[r0:r0 + chunk], nperseg, nhop, b0, b1)
+        out[r0:r0 + chunk] = _rows.spectro_correlate(S, ker)
+    return out if _is_tensor(data) else _to_host64(out)

@@ -198,14 +198,16 @@ def sosfiltfilt(sos, x, padlen=None):
 
 
 # ------------------------------------------------------------------------------ STFT magnitude
-def stft_mag(x, nfft, hop):
-    """|librosa.stft(y, n_fft=nfft, hop_length=hop)| for every row -> [nx, 1+nfft/2, 1+ns//hop]"""
+def stft_mag(x, nfft, hop, bin_lo=0, bin_hi=None):
+    """|librosa.stft(y, n_fft=nfft, hop_length=hop)| for every row, DFT bins bin_lo..bin_hi
+    -> [nx, bin_hi-bin_lo+1, 1+ns//hop]"""
     torch = _torch()
     dev = _check_input(x)
     nx, ns = x.shape
     plan = fft_plan(nfft, dev)
     nframes = 1 + ns // hop
-    out = torch.empty((nx, nfft // 2 + 1, nframes), dtype=torch.float32, device=x.device)
+    bin_hi = nfft // 2 if bin_hi is None else int(bin_hi)
+    out = torch.empty((nx, bin_hi - bin_lo + 1, nframes), dtype=torch.float32, device=x.device)
     key = ("hann", nfft, dev)
     if key not in _tab_cache:
         _tab_cache[key] = torch.from_numpy(sp.get_window("hann", nfft, fftbins=True).astype(np.float32)).to(x.device)
@@ -215,5 +217,44 @@ def stft_mag(x, nfft, hop):
         for r0 in range(0, nx, 65535):
             r1 = min(nx, r0 + 65535)
             _lib.check(L.d4w_stft_mag(plan.ptr, _lib.ptr(x[r0:r1], "float*"), _lib.ptr(out[r0:r1], "float*"), r1 - r0, ns,
-                                      int(hop), _lib.ptr(win, "float*"), _lib.stream_ptr()), "stft_mag")
+                                      int(hop), _lib.ptr(win, "float*"), int(bin_lo), bin_hi, _lib.stream_ptr()), "stft_mag")
+    return out
+
+
+# ------------------------------------------------------------------------------ spectrogram correlation
+def row_max(x2d):
+    """max over the last axis of a [rows, n] float32 CUDA tensor"""
+    torch = _torch()
+    rows_, n = x2d.shape
+    out = torch.empty(rows_, dtype=torch.float32, device=x2d.device)
+    with torch.cuda.device(x2d.device.index):
+        _lib.check(_lib.lib().d4w_row_max(_lib.ptr(x2d, "float*"), rows_, n, _lib.ptr(out, "float*"), _lib.stream_ptr()), "row_max")
+    return out
+
+
+def row_median(x2d):
+    """np.median over the last axis of a non-negative [rows, n] float32 CUDA tensor"""
+    torch = _torch()
+    rows_, n = x2d.shape
+    out = torch.empty(rows_, dtype=torch.float32, device=x2d.device)
+    with torch.cuda.device(x2d.device.index):
+        _lib.check(_lib.lib().d4w_row_median(_lib.ptr(x2d, "float*"), rows_, n, _lib.ptr(out, "float*"), _lib.stream_ptr()), "row_median")
+    return out
+
+
+def spectro_correlate(S, kernel, median=None):
+    """detect.xcorr2d for a batch: S [nx, nf, nt] float32 CUDA (un-normalised magnitudes are fine:
+    the max-normalisation of get_sliced_nspectrogram cancels against the median), kernel [nf, kw]."""
+    torch = _torch()
+    nx, nf, nt = S.shape
+    K = torch.from_numpy(np.ascontiguousarray(kernel, dtype=np.float32)).to(S.device)
+    if K.shape[0] != nf:
+        raise ValueError(f"kernel has {K.shape[0]} frequency rows, spectrogram slice has {nf}")
+    kw = K.shape[1]
+    if median is None:
+        median = row_median(S.reshape(nx, nf * nt))
+    out = torch.empty((nx, nt), dtype=torch.float32, device=S.device)
+    with torch.cuda.device(S.device.index):
+        _lib.check(_lib.lib().d4w_speccorr(_lib.ptr(S, "float*"), nx, nf, nt, _lib.ptr(K, "float*"), kw, _lib.ptr(median, "float*"),
+                                           _lib.ptr(out, "float*"), _lib.stream_ptr()), "speccorr")
     return out

@@ -134,9 +134,19 @@ int d4w_sosfiltfilt(const float* dev_x, float* dev_y, float* dev_tmp, int nx, in
 
 /* ---- batched STFT magnitude with librosa.stft framing (dsp.get_spectrogram dsp.py:66-68,
  *      detect.get_sliced_nspectrogram detect.py:382): centred frames, zero padding, window
- *      dev_window[n_fft]; dev_out: float32 [nx][n_fft/2+1][1 + ns/hop]. */
+ *      dev_window[n_fft]; only DFT bins bin_lo..bin_hi (inclusive) are written (the band slice of
+ *      detect.py:390-392): dev_out: float32 [nx][bin_hi-bin_lo+1][1 + ns/hop]. */
 int d4w_stft_mag(d4w_fft_plan* plan, const float* dev_x, float* dev_out, int nx, int ns, int hop,
-                 const float* dev_window, void* stream);
+                 const float* dev_window, int bin_lo, int bin_hi, void* stream);
+
+/* ---- spectrogram-correlation detector: detect.xcorr2d / compute_cross_correlogram_spectrocorr
+ *      (detect.py:579-602, :650-708).  Per-row median / maximum of a float32 matrix [nrows][n]
+ *      (entries must be >= 0 for the median), and
+ *      out[row][t] = max(0, sum_f sum_j S[row][f][t - kw/2 + j] K[f][j]) / (med[row] * kw). */
+int d4w_row_median(const float* dev_x, int nrows, size_t n, float* dev_median, void* stream);
+int d4w_row_max(const float* dev_x, int nrows, size_t n, float* dev_max, void* stream);
+int d4w_speccorr(const float* dev_S, int nx, int nf, int nt, const float* dev_K, int kw, const float* dev_median,
+                 float* dev_out, void* stream);
 /* D4W_CDEF_END */
 
 #ifdef __cplusplus

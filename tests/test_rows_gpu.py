@@ -132,3 +132,40 @@ def test_stft_batched(dw):
         ref = np.abs(O.stft_librosa(x[i].astype(np.float64), 160, 8))
         assert mag[i].shape == ref.shape
         assert rel_err(mag[i], ref)[0] <= 2e-5
+
+
+def test_spectrocorr_pieces_golden(dw, golden):
+    g = golden("spectrocorr")
+    _, _, ker = dw.detect.buildkernel(27., 16., 4., 0.9, g["ff"], g["tt"], FS, 12., 36.)
+    assert rel_err(ker, g["ker"])[0] <= 1e-14
+    out = dw.detect.xcorr2d(g["S"], g["ker"])
+    assert rel_err(out, g["xc2d"])[0] <= 2e-5
+
+
+@pytest.mark.parametrize("kern", [{'f0': 27., 'f1': 17., 'dur': 0.8, 'bdwidth': 4.}, {'f0': 20., 'f1': 14., 'dur': 1.2, 'bdwidth': 4.}])
+def test_spectrocorr_detector_vs_oracle(dw, kern):
+    """scripts/main_spectrodetect.py:100-107 parameters on a small synthetic matrix."""
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal((6, 9000)).astype(np.float32)
+    flims = [14., 30.]
+    out = dw.detect.compute_cross_correlogram_spectrocorr(x, FS, flims, kern, 0.8, 0.95)
+    ref = D.compute_cross_correlogram_spectrocorr(x.astype(np.float64), FS, flims, kern, 0.8, 0.95)
+    assert out.shape == ref.shape
+    e = rel_err(out, ref)
+    assert e[0] <= TOL and e[1] <= TOL, e
+    # the single-trace helper keeps the reference's return order (spectrogram, ff, tt)
+    p, ff, tt = dw.detect.get_sliced_nspectrogram(x[0], FS, 2., 32., 160, 8)
+    pr, ffr, ttr = D.get_sliced_nspectrogram(x[0].astype(np.float64), FS, 2., 32., 160, 8)
+    assert p.shape == pr.shape and np.allclose(ff, ffr) and np.allclose(tt, ttr)
+    assert rel_err(p, pr)[0] <= 2e-5
+
+
+def test_row_median_exact(dw):
+    import torch
+    from das4whales_b200 import rows
+    rng = np.random.default_rng(5)
+    for n in (7, 1000, 4097, 150001):
+        a = np.abs(rng.standard_normal((3, n))).astype(np.float32)
+        a[1, : n // 3] = 0.25                     # many ties
+        med = rows.row_median(torch.from_numpy(a).cuda()).cpu().numpy()
+        assert np.array_equal(med, np.median(a, axis=1).astype(np.float32)), n
