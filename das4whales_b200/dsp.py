@@ -92,6 +92,100 @@ def hybrid_ninf_filter_design(trace_shape, selected_channels, dx, fs, cs_min=140
     return mask
 
 
+
+def _shifted_axes(trace_shape, selected_channels, dx, fs):
+    nnx, nns = trace_shape
+    freq = np.fft.fftshift(np.fft.fftfreq(nns, d=1 / fs))
+    knum = np.fft.fftshift(np.fft.fftfreq(nnx, d=selected_channels[2] * dx))
+    return freq, knum
+
+
+def hybrid_filter_design(trace_shape, selected_channels, dx, fs, cs_min=1400., cp_min=1450., fmin=15., fmax=25.,
+                         display_filter=False):
+    """Infinite-speed hybrid mask, sine tapers in f and k (reference: dsp.py:174-305).  Built on the
+    host at design time (vectorised) and applied through the dense-mask GPU path."""
+    freq, knum = _shifted_axes(trace_shape, selected_channels, dx, fs)
+    fpmin, fpmax = fmin - 4, fmax + 4                          # df_taper = 4 Hz (dsp.py:216)
+    H = np.zeros_like(freq)
+    up = (freq >= fpmin) & (freq <= fmin)
+    H[up] = np.sin(0.5 * np.pi * (freq[up] - fpmin) / (fmin - fpmin))
+    H[(freq >= fmin) & (freq <= fmax)] = 1
+    dn = (freq >= fmax) & (freq <= fpmax)
+    H[dn] = np.cos(0.5 * np.pi * (freq[dn] - fmax) / (fmax - fpmax))
+    lo, hi = int(np.argmax(freq >= fpmin)), int(np.argmax(freq >= fpmax))
+    f = freq[lo:hi][None, :]
+    k = knum[:, None]
+    ks, kp = f / cs_min, f / cp_min
+    col = np.zeros((len(knum), hi - lo))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        neg = (k >= -ks) & (k <= -kp) & (ks != kp)
+        col = np.where(neg, -np.sin(0.5 * np.pi * (k + ks) / (kp - ks)), col)
+        pos = (-k >= -ks) & (-k <= -kp) & (ks != kp)
+        col = np.where(pos, np.sin(0.5 * np.pi * (k - ks) / (kp - ks)), col)
+    col = np.where((k < kp) & (k > -kp), 1.0, col)
+    M = np.tile(H, (len(knum), 1))
+    M[:, lo:hi] *= col
+    M = M + M[:, ::-1]                                         # np.fliplr symmetrisation (dsp.py:264)
+    mask = _fk.FkMask.from_dense(M)
+    if display_filter:
+        _display_mask(mask, freq, knum)
+    return mask
+
+
+def _gs_start(trace_shape, selected_channels, dx, fs, fmin, fmax):
+    freq, knum = _shifted_axes(trace_shape, selected_channels, dx, fs)
+    H = np.zeros_like(freq)
+    H[(freq >= fmin) & (freq <= fmax)] = 1
+    lo, hi = int(np.argmax(freq >= fmin - 4)), int(np.argmax(freq >= fmax + 4))
+    return freq, knum, np.tile(H, (len(knum), 1)), lo, hi
+
+
+def hybrid_gs_filter_design(trace_shape, selected_channels, dx, fs, cs_min=1400., cp_min=1450., fmin=15., fmax=25.,
+                            display_filter=False):
+    """Infinite-speed hybrid mask with Gaussian (sigma = 20 bins) tapers (reference: dsp.py:457-579)."""
+    from scipy import ndimage
+    freq, knum, M, lo, hi = _gs_start(trace_shape, selected_channels, dx, fs, fmin, fmax)
+    kp = freq[lo:hi][None, :] / cp_min
+    M[:, lo:hi] *= ((knum[:, None] < kp) & (knum[:, None] > -kp))
+    M = ndimage.gaussian_filter(M + M[:, ::-1], 20)            # dsp.py:539-540
+    mask = _fk.FkMask.from_dense(M)
+    if display_filter:
+        _display_mask(mask, freq, knum)
+    return mask
+
+
+def hybrid_ninf_gs_filter_design(trace_shape, selected_channels, dx, fs, cs_min=1400., cp_min=1450., cp_max=3400,
+                                 cs_max=3500, fmin=15., fmax=25., display_filter=False):
+    """Finite-speed hybrid mask with Gaussian tapers (reference: dsp.py:582-702)."""
+    from scipy import ndimage
+    freq, knum, M, lo, hi = _gs_start(trace_shape, selected_channels, dx, fs, fmin, fmax)
+    f = freq[lo:hi][None, :]
+    M[:, lo:hi] *= ((knum[:, None] > -f / cp_min) & (knum[:, None] < -f / cp_max))
+    M = ndimage.gaussian_filter(M, 20)                         # dsp.py:659
+    M = M + M[:, ::-1]
+    M = M + M[::-1, :]
+    mask = _fk.FkMask.from_dense(M)
+    if display_filter:
+        _display_mask(mask, freq, knum)
+    return mask
+
+
+def fk_filt(data, tint, fs, xint, dx, c_min, c_max):
+    """Legacy one-call f-k filter: Gaussian-blurred boolean fan built and applied in one go
+    (reference: dsp.py:883-953).  The fan is built on the host, the 2-D filtering runs on the GPU."""
+    from scipy import ndimage
+    shape = tuple(data.shape)
+    f = np.fft.fftshift(np.fft.fftfreq(shape[1], d=tint / fs))
+    k = np.fft.fftshift(np.fft.fftfreq(shape[0], d=xint * dx))
+    ff, kk = np.meshgrid(f, k)
+    g = 1.0 * ((ff < kk * c_min) & (ff < -kk * c_min))
+    g2 = 1.0 * ((ff < kk * c_max) & (ff < -kk * c_max))
+    g = g + g[:, ::-1] - (g2 + g2[:, ::-1])
+    g = ndimage.gaussian_filter(g, 20)
+    g = (g - np.min(g)) / (np.max(g) - np.min(g))
+    return fk_filter_filt(data, _fk.FkMask.from_dense(g))
+
+
 def _display_mask(mask, freq, knum):
     import matplotlib.pyplot as plt
     m = np.asarray(mask)

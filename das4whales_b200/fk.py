@@ -120,9 +120,20 @@ class FkMask:
         if dm is None:
             if (plan.nx, plan.ns) != self.shape:
                 raise ValueError(f"operands could not be broadcast together with shapes ({plan.nx},{plan.ns}) {self.shape}")
-            dm = _DeviceMask(plan, self._create)
+            if self.kind == "dense":      # design functions without a closed form on the device
+                dm = _DenseMaskHolder(plan, _dense_to_device(self._dense, plan.device)).dm
+            else:
+                dm = _DeviceMask(plan, self._create)
             self._dev[id(plan)] = dm
         return dm
+
+    @classmethod
+    def from_dense(cls, array):
+        """Wrap a dense [channel x time] mask (reference shifted layout) in the sparse.COO-like API."""
+        a = np.asarray(array, dtype=np.float64)
+        m = cls("dense", a.shape, {}, order="C")
+        m._dense = a
+        return m
 
     # ---- host side (what plots / prints see) -------------------------------------------
     def todense(self):

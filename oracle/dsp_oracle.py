@@ -118,6 +118,63 @@ def hybrid_filter_design(trace_shape, selected_channels, dx, fs, cs_min=1400., c
     return M + M[:, ::-1]
 
 
+
+def _gs_band(trace_shape, selected_channels, dx, fs, fmin, fmax):
+    nx, ns = trace_shape
+    freq, knum = _axes(trace_shape, selected_channels, dx, fs)
+    H = np.zeros_like(freq)
+    H[(freq >= fmin) & (freq <= fmax)] = 1
+    i0 = int(np.argmax(freq >= fmin - 4))
+    i1 = int(np.argmax(freq >= fmax + 4))
+    return freq, knum, np.tile(H, (nx, 1)), i0, i1
+
+
+def hybrid_gs_filter_design(trace_shape, selected_channels, dx, fs, cs_min=1400., cp_min=1450., fmin=15., fmax=25.):
+    """Boolean band (|k| < f/cp_min) blurred with a sigma=20 Gaussian -- dsp.py:457-579 (dense)."""
+    from scipy import ndimage
+    freq, knum, M, i0, i1 = _gs_band(trace_shape, selected_channels, dx, fs, fmin, fmax)
+    for i in range(i0, i1):
+        kp = freq[i] / cp_min
+        M[:, i] *= ((knum < kp) & (knum > -kp)).astype(float)
+    M = M + M[:, ::-1]
+    return ndimage.gaussian_filter(M, 20)
+
+
+def hybrid_ninf_gs_filter_design(trace_shape, selected_channels, dx, fs, cs_min=1400., cp_min=1450., cp_max=3400,
+                                 cs_max=3500, fmin=15., fmax=25.):
+    """Boolean band (-f/cp_min < k < -f/cp_max), Gaussian sigma=20, then fliplr / flipud sums
+    -- dsp.py:582-702 (dense)."""
+    from scipy import ndimage
+    freq, knum, M, i0, i1 = _gs_band(trace_shape, selected_channels, dx, fs, fmin, fmax)
+    for i in range(i0, i1):
+        M[:, i] *= ((knum > -freq[i] / cp_min) & (knum < -freq[i] / cp_max)).astype(float)
+    M = ndimage.gaussian_filter(M, 20)
+    M = M + M[:, ::-1]
+    return M + M[::-1, :]
+
+
+def fk_filt_mask(shape, tint, fs, xint, dx, c_min, c_max):
+    """The Gaussian-blurred fan the legacy dsp.fk_filt builds and applies -- dsp.py:883-953."""
+    from scipy import ndimage
+    nx, ns = shape
+    f = np.fft.fftshift(np.fft.fftfreq(ns, d=tint / fs))
+    k = np.fft.fftshift(np.fft.fftfreq(nx, d=xint * dx))
+    ff, kk = np.meshgrid(f, k)
+    g = 1.0 * ((ff < kk * c_min) & (ff < -kk * c_min))
+    g2 = 1.0 * ((ff < kk * c_max) & (ff < -kk * c_max))
+    g = g + g[:, ::-1]
+    g = g - (g2 + g2[:, ::-1])
+    g = ndimage.gaussian_filter(g, 20)
+    return (g - np.min(g)) / (np.max(g) - np.min(g))
+
+
+def fk_filt(data, tint, fs, xint, dx, c_min, c_max):
+    """Legacy one-call f-k filter -- dsp.py:883-953."""
+    data = np.asarray(data, dtype=np.float64)
+    g = fk_filt_mask(data.shape, tint, fs, xint, dx, c_min, c_max)
+    return np.fft.ifft2(np.fft.ifftshift(np.fft.fftshift(np.fft.fft2(data)) * g)).real
+
+
 def fold_mask(mask_shifted):
     """Hermitian fold of a shifted-layout mask.
 

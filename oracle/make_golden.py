@@ -74,6 +74,18 @@ def main():
         o = O.hybrid_filter_design((nx, ns), sel, DX, FS, 1400., 1450., 15., 25.)
         rep[f"hyb_{nx}x{ns}"] = close(r, o, what="hybrid_filter_design")
         masks[f"hyb_{nx}x{ns}"] = r
+    for (nx, ns) in [(40, 240)]:
+        sel = [0, nx, 1]
+        r = np.asarray(dsp.hybrid_gs_filter_design((nx, ns), sel, DX, FS, 1400., 1450., 15., 25.))
+        rep[f"gs_{nx}x{ns}"] = close(r, O.hybrid_gs_filter_design((nx, ns), sel, DX, FS, 1400., 1450., 15., 25.), what="hybrid_gs")
+        masks[f"gs_{nx}x{ns}"] = r
+        r = np.asarray(dsp.hybrid_ninf_gs_filter_design((nx, ns), sel, DX, FS, 1400., 1450., 3400, 3500, 15., 25.))
+        rep[f"ninfgs_{nx}x{ns}"] = close(r, O.hybrid_ninf_gs_filter_design((nx, ns), sel, DX, FS, 1400., 1450., 3400, 3500, 15., 25.), what="hybrid_ninf_gs")
+        masks[f"ninfgs_{nx}x{ns}"] = r
+    xl = synth(40, 240, seed=77)
+    rl = dsp.fk_filt(xl, 1, FS, 1, DX, 1450., 3400.)
+    rep["fk_filt_legacy"] = close(rl, O.fk_filt(xl, 1, FS, 1, DX, 1450., 3400.), what="legacy fk_filt")
+    masks["legacy_x"], masks["legacy_y"] = xl, rl
     np.savez_compressed(os.path.join(OUT, "masks.npz"), **masks)
 
     # ---- f-k apply (a3-a5) ----------------------------------------------------------

@@ -164,3 +164,18 @@ def test_full_size_properties(dw):
     ysh = flt(sh)
     cov = float((ysh - torch.roll(yb, shifts=(37, 1001), dims=(0, 1))).abs().max()) / scale
     assert cov <= 2e-5, cov
+
+
+def test_dense_design_masks_and_legacy_fk_filt(dw, golden):
+    """hybrid / gs designs go through the dense-mask GPU path; legacy dsp.fk_filt reuses it."""
+    g = golden("masks")
+    rng = np.random.default_rng(2)
+    x = rng.standard_normal((40, 240)).astype(np.float32)
+    sel = [0, 40, 1]
+    for mask in (dw.dsp.hybrid_filter_design((40, 240), sel, DX, FS), dw.dsp.hybrid_gs_filter_design((40, 240), sel, DX, FS),
+                 dw.dsp.hybrid_ninf_gs_filter_design((40, 240), sel, DX, FS)):
+        y = dw.dsp.fk_filter_sparsefilt(x, mask)
+        ref = O.fk_filter_filt(x.astype(np.float64), mask.todense())
+        assert rel_err(y, ref)[0] <= TOL
+    y = dw.dsp.fk_filt(g["legacy_x"], 1, FS, 1, DX, 1450., 3400.)
+    assert rel_err(y, g["legacy_y"])[0] <= TOL

@@ -14,6 +14,8 @@ FS = 200.0
 def test_masks_match_golden(golden):
     g = golden("masks")
     for key in g.files:
+        if key.startswith("legacy"):
+            continue
         kind, shape = key.split("_")[0], key.split("_")[1]
         nx, ns = (int(v) for v in shape.split("x"))
         step = int(key.split("_s")[1]) if "_s" in key else 1
@@ -22,9 +24,14 @@ def test_masks_match_golden(golden):
             m = O.fk_filter_design((nx, ns), sel, DX, FS, 1400, 1450, 3400, 3500)
         elif kind == "ninf":
             m = O.hybrid_ninf_filter_design((nx, ns), sel, DX, FS, 1350., 1450., 3300, 3450, 14., 30.)
+        elif kind == "gs":
+            m = O.hybrid_gs_filter_design((nx, ns), sel, DX, FS, 1400., 1450., 15., 25.)
+        elif kind == "ninfgs":
+            m = O.hybrid_ninf_gs_filter_design((nx, ns), sel, DX, FS, 1400., 1450., 3400, 3500, 15., 25.)
         else:
             m = O.hybrid_filter_design((nx, ns), sel, DX, FS, 1400., 1450., 15., 25.)
         assert np.max(np.abs(m - g[key])) <= 1e-13, key
+    assert rel_err(O.fk_filt(g["legacy_x"], 1, FS, 1, DX, 1450., 3400.), g["legacy_y"])[0] <= 1e-12
 
 
 def test_fk_apply_matches_golden(golden):
