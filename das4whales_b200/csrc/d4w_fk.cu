@@ -274,59 +274,67 @@ static int launch_row_split(const d4w_fk_plan* pl, float2* w, int nact, cudaStre
     return D4W_OK;
 }
 
-extern "C" int d4w_fk_apply_pass(d4w_fk_plan* pl, d4w_fk_mask* m, const float* x, float* y, void* ws, int taper,
-                                 int pass, void* stream_v) {
+// Geometry `pl` may be a different plan than the mask's when a matrix is sharded over GPUs:
+//  * passes 1 / 5 run on a time slab [nx][pl->ns] that starts at global sample t_offset (all kept rows);
+//  * passes 2-4 run on `slot_count` kept rows starting at slot `slot_begin` (full time axis), `ws`
+//    pointing at the first local row.
+extern "C" int d4w_fk_apply_pass_ex(d4w_fk_plan* pl, d4w_fk_mask* m, const float* x, float* y, void* ws, int taper,
+                                    int pass, int slot_begin, int slot_count, int t_offset, void* stream_v) {
     if (!pl || !m || !ws) return fail(D4W_ERR_ARG, "d4w_fk_apply: null argument");
-    if (m->plan != pl) return fail(D4W_ERR_ARG, "d4w_fk_apply: mask was built for a different plan");
+    d4w_fk_plan* mp = m->plan;
     if (!m->d_table) return fail(D4W_ERR_ARG, "d4w_fk_apply: call d4w_fk_mask_build first");
+    if (pl->device != mp->device) return fail(D4W_ERR_ARG, "d4w_fk_apply: plan and mask live on different devices");
     DeviceGuard guard(pl->device);
     cudaStream_t stream = (cudaStream_t)stream_v;
     float2* w = (float2*)ws;
     const size_t ldw = (size_t)pl->ns;
-    const int tile = 2 * pl->col.nc;
-    const int ntiles = (pl->ns + tile - 1) / tile;
     const int nact = m->nact;
+    if (pass == 1 || pass == 5) {
+        if (pl->nx != mp->nx) return fail(D4W_ERR_ARG, "d4w_fk_apply: column passes need the mask's channel count");
+        if (t_offset < 0 || (long long)t_offset + pl->ns > mp->ns) return fail(D4W_ERR_ARG, "d4w_fk_apply: time slab outside the mask's time axis");
+    } else {
+        if (pl->ns != mp->ns) return fail(D4W_ERR_ARG, "d4w_fk_apply: time passes need the mask's full time axis");
+        if (slot_begin < 0 || slot_count < 0 || slot_begin + slot_count > nact) return fail(D4W_ERR_ARG, "d4w_fk_apply: bad slot range");
+    }
+    const int tile = pl->col.dual ? 4 * pl->col.npair : 2 * pl->col.nc;
+    const int ntiles = (pl->ns + tile - 1) / tile;
+    const float* tap = taper ? mp->d_taper + t_offset : nullptr;
     switch (pass) {
         case 1:
             if (!x) return fail(D4W_ERR_ARG, "d4w_fk_apply: null input");
             if (nact == 0) return D4W_OK;
             if (pl->col.dual && pl->col_threads <= 256)
-                k_col_fwd_dual<256><<<ntiles, pl->col_threads, pl->col_smem, stream>>>(pl->col, x, w, ldw, m->d_slot_pos, nact,
-                                                                                       taper ? pl->d_taper : nullptr);
+                k_col_fwd_dual<256><<<ntiles, pl->col_threads, pl->col_smem, stream>>>(pl->col, x, w, ldw, m->d_slot_pos, nact, tap);
             else if (pl->col.dual)
-                k_col_fwd_dual<512><<<ntiles, std::min(pl->col_threads, 512), pl->col_smem, stream>>>(
-                    pl->col, x, w, ldw, m->d_slot_pos, nact, taper ? pl->d_taper : nullptr);
+                k_col_fwd_dual<512><<<ntiles, std::min(pl->col_threads, 512), pl->col_smem, stream>>>(pl->col, x, w, ldw, m->d_slot_pos, nact, tap);
             else if (pl->col_threads <= 256)
-                k_col_fwd<256><<<ntiles, pl->col_threads, pl->col_smem, stream>>>(pl->col, x, w, ldw, m->d_slot_pos, nact,
-                                                                                  taper ? pl->d_taper : nullptr);
+                k_col_fwd<256><<<ntiles, pl->col_threads, pl->col_smem, stream>>>(pl->col, x, w, ldw, m->d_slot_pos, nact, tap);
             else if (pl->col_threads <= 512)
-                k_col_fwd<512><<<ntiles, pl->col_threads, pl->col_smem, stream>>>(pl->col, x, w, ldw, m->d_slot_pos, nact,
-                                                                                  taper ? pl->d_taper : nullptr);
+                k_col_fwd<512><<<ntiles, pl->col_threads, pl->col_smem, stream>>>(pl->col, x, w, ldw, m->d_slot_pos, nact, tap);
             else
-                k_col_fwd<1024><<<ntiles, pl->col_threads, pl->col_smem, stream>>>(pl->col, x, w, ldw, m->d_slot_pos, nact,
-                                                                                   taper ? pl->d_taper : nullptr);
+                k_col_fwd<1024><<<ntiles, pl->col_threads, pl->col_smem, stream>>>(pl->col, x, w, ldw, m->d_slot_pos, nact, tap);
             D4W_CHECK_LAUNCH("k_col_fwd");
             return D4W_OK;
         case 2:
-            if (pl->t1 == 1 || nact == 0) return D4W_OK;
-            return launch_row_split<false>(pl, w, nact, stream);
+            if (pl->t1 == 1 || slot_count == 0) return D4W_OK;
+            return launch_row_split<false>(pl, w, slot_count, stream);
         case 3: {
-            if (nact == 0) return D4W_OK;
-            dim3 grid(pl->t1, nact);
-            k_row_mid<<<grid, pl->row_threads, pl->row_smem, stream>>>(pl->row, w, ldw, m->d_table, (size_t)pl->ns);
+            if (slot_count == 0) return D4W_OK;
+            dim3 grid(pl->t1, slot_count);
+            k_row_mid<<<grid, pl->row_threads, pl->row_smem, stream>>>(pl->row, w, ldw, m->d_table + (size_t)slot_begin * pl->ns,
+                                                                       (size_t)pl->ns);
             D4W_CHECK_LAUNCH("k_row_mid");
             return D4W_OK;
         }
         case 4:
-            if (pl->t1 == 1 || nact == 0) return D4W_OK;
-            return launch_row_split<true>(pl, w, nact, stream);
+            if (pl->t1 == 1 || slot_count == 0) return D4W_OK;
+            return launch_row_split<true>(pl, w, slot_count, stream);
         case 5:
             if (!y) return fail(D4W_ERR_ARG, "d4w_fk_apply: null output");
             if (pl->col.dual && pl->col_threads <= 256)
                 k_col_inv_dual<256><<<ntiles, pl->col_threads, pl->col_smem, stream>>>(pl->col, w, ldw, m->d_slot_pos, nact, y);
             else if (pl->col.dual)
-                k_col_inv_dual<512><<<ntiles, std::min(pl->col_threads, 512), pl->col_smem, stream>>>(pl->col, w, ldw,
-                                                                                                     m->d_slot_pos, nact, y);
+                k_col_inv_dual<512><<<ntiles, std::min(pl->col_threads, 512), pl->col_smem, stream>>>(pl->col, w, ldw, m->d_slot_pos, nact, y);
             else if (pl->col_threads <= 256)
                 k_col_inv<256><<<ntiles, pl->col_threads, pl->col_smem, stream>>>(pl->col, w, ldw, m->d_slot_pos, nact, y);
             else if (pl->col_threads <= 512)
@@ -338,6 +346,13 @@ extern "C" int d4w_fk_apply_pass(d4w_fk_plan* pl, d4w_fk_mask* m, const float* x
         default:
             return fail(D4W_ERR_ARG, "d4w_fk_apply_pass: pass must be 1..5");
     }
+}
+
+extern "C" int d4w_fk_apply_pass(d4w_fk_plan* pl, d4w_fk_mask* m, const float* x, float* y, void* ws, int taper,
+                                 int pass, void* stream) {
+    if (!pl || !m) return fail(D4W_ERR_ARG, "d4w_fk_apply: null argument");
+    if (m->plan != pl) return fail(D4W_ERR_ARG, "d4w_fk_apply: mask was built for a different plan");
+    return d4w_fk_apply_pass_ex(pl, m, x, y, ws, taper, pass, 0, m->nact, 0, stream);
 }
 
 extern "C" int d4w_fk_apply(d4w_fk_plan* pl, d4w_fk_mask* m, const float* x, float* y, void* ws, int taper,

@@ -89,6 +89,13 @@ int d4w_fk_apply(d4w_fk_plan* plan, d4w_fk_mask* mask, const float* dev_x, float
 /* the five passes, separately (bench / profiling): pass = 1..5 */
 int d4w_fk_apply_pass(d4w_fk_plan* plan, d4w_fk_mask* mask, const float* dev_x, float* dev_y,
                       void* dev_workspace, int taper, int pass, void* stream);
+/* sharded variant (one matrix over several GPUs, das4whales_b200/dist.py): `plan` gives the local
+ * geometry -- passes 1/5 on a time slab [nx][plan.ns] starting at global sample t_offset with all kept
+ * rows; passes 2-4 on kept rows [slot_begin, slot_begin+slot_count) over the full time axis, the
+ * workspace pointing at the first local row.  The mask is the one of the full matrix. */
+int d4w_fk_apply_pass_ex(d4w_fk_plan* plan, d4w_fk_mask* mask, const float* dev_x, float* dev_y,
+                         void* dev_workspace, int taper, int pass, int slot_begin, int slot_count,
+                         int t_offset, void* stream);
 
 /* ---- generic shared-memory FFT plan (matched-filter blocks, STFT frames) ----------------- */
 typedef struct d4w_fft_plan d4w_fft_plan;
