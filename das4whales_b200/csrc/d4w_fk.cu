@@ -6,6 +6,8 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <cstdint>
+#include <cuda.h>
 #include "d4w_common.hpp"
 #include "fk_hostplan.hpp"
 #include "fk_kernels.cuh"
@@ -21,8 +23,41 @@ extern "C" const char* d4w_last_error(void) { return last_error_ref().c_str(); }
 extern "C" int d4w_version(void) { return 100; }
 extern "C" long long d4w_launch_count(void) { return launch_counter().load(); }
 
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_tiled() {
+    static PFN_encodeTiled fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled)p;
+        else
+            (void)cudaGetLastError();
+    }
+    return fn;
+}
+
+// 2-D fp32 tensor map over a [nx][ns] row-major matrix, box = 4 samples x 256 channels
+static bool make_tile_map(CUtensorMap* map, const float* base, int nx, int ns) {
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (!enc) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)ns, (cuuint64_t)nx};
+    const cuuint64_t strides[1] = {(cuuint64_t)ns * sizeof(float)};
+    const cuuint32_t box[2] = {4, (cuuint32_t)kTmaBoxRows};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 struct d4w_fk_plan {
     int nx = 0, ns = 0, device = 0;
+    int num_sms = 148;
     int t1 = 1, t2 = 0;
     ColParams col{};
     RowParams row{};
@@ -57,14 +92,16 @@ extern "C" int d4w_fk_plan_create(d4w_fk_plan** out, int nx, int ns, int device)
     cudaDeviceProp prop;
     D4W_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     const size_t smem_cap = prop.sharedMemPerBlockOptin;
+    const int num_sms = prop.multiProcessorCount;
 
     FkHostPlan hp;
     std::string err;
     if (build_fk_hostplan(nx, ns, smem_cap, hp, err)) return fail(D4W_ERR_UNSUPPORTED, err);
     auto pl = new d4w_fk_plan();
-    pl->nx = nx; pl->ns = ns; pl->device = device;
+    pl->nx = nx; pl->ns = ns; pl->device = device; pl->num_sms = num_sms;
     pl->col.pl = hp.colpl; pl->col.nx = nx; pl->col.ns = ns; pl->col.nc = hp.nc; pl->col.nc_shift = hp.nc_shift;
     pl->col.fstride = hp.fstride; pl->col.aligned = hp.aligned;
+    pl->col.tma = hp.tma;
     pl->col.dual = hp.dual; pl->col.npair = hp.npair; pl->col.npair_shift = hp.npair_shift; pl->col.aligned16 = hp.aligned16;
     pl->col_smem = hp.col_smem;
     pl->col_threads = std::min(1024, std::max(32, env_int("D4W_COL_THREADS", 512) / 32 * 32));
@@ -93,6 +130,8 @@ extern "C" int d4w_fk_plan_create(d4w_fk_plan** out, int nx, int ns, int device)
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_col_inv_dual<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_col_fwd_dual<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_col_inv_dual<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_col_fwd_tma<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap - 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_col_inv_tma<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap - 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_col_fwd<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_col_inv<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_row_mid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
@@ -303,6 +342,16 @@ extern "C" int d4w_fk_apply_pass_ex(d4w_fk_plan* pl, d4w_fk_mask* m, const float
         case 1:
             if (!x) return fail(D4W_ERR_ARG, "d4w_fk_apply: null input");
             if (nact == 0) return D4W_OK;
+            if (pl->col.tma && ((uintptr_t)x % 16 == 0)) {
+                CUtensorMap tm;
+                if (make_tile_map(&tm, x, pl->nx, pl->ns)) {
+                    const int grid = std::min(ntiles, pl->num_sms);
+                    k_col_fwd_tma<512><<<grid, std::min(pl->col_threads, 512), pl->col_smem, stream>>>(tm, pl->col, w, ldw, m->d_slot_pos,
+                                                                                                   nact, tap, ntiles);
+                    D4W_CHECK_LAUNCH("k_col_fwd_tma");
+                    return D4W_OK;
+                }
+            }
             if (pl->col.dual && pl->col_threads <= 256)
                 k_col_fwd_dual<256><<<ntiles, pl->col_threads, pl->col_smem, stream>>>(pl->col, x, w, ldw, m->d_slot_pos, nact, tap);
             else if (pl->col.dual)
@@ -331,6 +380,16 @@ extern "C" int d4w_fk_apply_pass_ex(d4w_fk_plan* pl, d4w_fk_mask* m, const float
             return launch_row_split<true>(pl, w, slot_count, stream);
         case 5:
             if (!y) return fail(D4W_ERR_ARG, "d4w_fk_apply: null output");
+            if (pl->col.tma && ((uintptr_t)y % 16 == 0)) {
+                CUtensorMap tm;
+                if (make_tile_map(&tm, y, pl->nx, pl->ns)) {
+                    const int grid = std::min(ntiles, pl->num_sms);
+                    k_col_inv_tma<512><<<grid, std::min(pl->col_threads, 512), pl->col_smem, stream>>>(tm, pl->col, w, ldw, m->d_slot_pos,
+                                                                                                   nact, ntiles);
+                    D4W_CHECK_LAUNCH("k_col_inv_tma");
+                    return D4W_OK;
+                }
+            }
             if (pl->col.dual && pl->col_threads <= 256)
                 k_col_inv_dual<256><<<ntiles, pl->col_threads, pl->col_smem, stream>>>(pl->col, w, ldw, m->d_slot_pos, nact, y);
             else if (pl->col.dual)

@@ -10,7 +10,7 @@ namespace d4w {
 struct FkHostPlan {
     int nx = 0, ns = 0;
     int t1 = 1, t2 = 0, nc = 1, nc_shift = 0, fstride = 0, aligned = 0;
-    int dual = 0, npair = 0, npair_shift = 0, aligned16 = 0;
+    int dual = 0, npair = 0, npair_shift = 0, aligned16 = 0, tma = 0;
     FftPlan colpl{}, rowpl{};
     std::vector<float2> tw_col, tw_row, twT;
     std::vector<int> pos2k, k2pos, pos2k_row;
@@ -71,6 +71,10 @@ inline int build_fk_hostplan(int nx, int ns, size_t smem_cap, FkHostPlan& hp, st
     hp.npair = nc / 2;
     hp.npair_shift = (hp.npair <= 1) ? 0 : (hp.npair == 2) ? 1 : 2;
     hp.aligned16 = (ns % 4 == 0) ? 1 : 0;
+    // TMA path: one dual column per tile, rows 16-byte aligned; tile padded to whole 256-row boxes
+    hp.tma = (hp.dual && hp.npair == 1 && hp.aligned16 && env_int("D4W_COL_TMA", 1) &&
+              (size_t)((nx + 255) / 256 * 256) * 16 <= smem_cap - 1024) ? 1 : 0;
+    if (hp.tma) { hp.fstride = (nx + 255) / 256 * 256; hp.col_smem = (size_t)hp.fstride * 16; }
     if (!make_plan(nx, hp.dual ? std::min(col_maxr, 16) : col_maxr, hp.colpl, e2)) { err = "channel axis: " + e2; return 1; }
 
     int t1 = 0;

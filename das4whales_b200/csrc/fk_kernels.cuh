@@ -33,6 +33,7 @@ struct ColParams {
     int dual;              // 1: dual-lane (f32x2) kernels, tile = 4*npair samples stored as cpd elements
     int npair, npair_shift;
     int aligned16;         // rows 16-byte aligned (ns % 4 == 0)
+    int tma;               // 1: TMA-fed persistent kernels (npair == 1, ns % 4 == 0)
 };
 
 struct RowParams {
@@ -418,7 +419,7 @@ __host__ __device__ inline void body_row_mid(const RowParams& rp, float2* __rest
 
 // ================================================================== __global__ wrappers
 #ifdef __CUDACC__
-extern __shared__ __align__(16) float2 d4w_dyn_smem[];
+extern __shared__ __align__(1024) float2 d4w_dyn_smem[];
 
 template <int MAXT>
 static __global__ void __launch_bounds__(MAXT, 1)
@@ -447,6 +448,130 @@ k_col_inv_dual(ColParams cp, const float2* __restrict__ w, size_t ldw, const int
                float* __restrict__ y) {
     body_col_inv_dual(cp, w, ldw, slot_pos, nact, y, blockIdx.x, threadIdx.x, blockDim.x, reinterpret_cast<cpd*>(d4w_dyn_smem));
 }
+
+
+// ================================================================== TMA-fed persistent column kernels
+// Blackwell path for the dominant case (one dual column per tile, ns % 4 == 0): the whole
+// [nx x 4 samples] tile moves with 2-D tensor copies (cp.async.bulk.tensor, boxes of 256 rows x 16 B)
+// issued by one thread -- no per-row LSU instruction, completion through an mbarrier (load) or a
+// bulk group (store, fully asynchronous w.r.t. the next tile).  CTAs are persistent (one per SM).
+#ifdef __CUDACC__
+#include <cuda.h>
+
+constexpr int kTmaBoxRows = 256;
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra.uni WAIT_DONE;\n"
+        "bra.uni WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int c0, int c1, const void* smem_src) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(c0), "r"(c1),
+                 "r"(smem_u32(smem_src))
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// forward: x --TMA--> smem, forward stages, untangle + pruned store (same math as body_col_fwd_dual)
+template <int MAXT>
+static __global__ void __launch_bounds__(MAXT, 1)
+k_col_fwd_tma(const __grid_constant__ CUtensorMap tmx, ColParams cp, float2* __restrict__ w, size_t ldw,
+              const int2* __restrict__ slot_pos, int nact, const float* __restrict__ taper, int ntiles) {
+    cpd* smem = reinterpret_cast<cpd*>(d4w_dyn_smem);
+    __shared__ __align__(8) unsigned long long bar;
+    const int tid = threadIdx.x, nthr = blockDim.x, nx = cp.nx, ns = cp.ns;
+    const int nbox = (nx + kTmaBoxRows - 1) / kTmaBoxRows;
+    if (tid == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    __syncthreads();
+    unsigned parity = 0;
+    const f2x half = vbc(0.5f);
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int t0 = tile * 4;
+        if (tid == 0) {
+            mbar_expect_tx(&bar, (unsigned)(nbox * kTmaBoxRows * 16));
+            for (int b = 0; b < nbox; ++b) tma_load_2d(smem + b * kTmaBoxRows, &tmx, t0, b * kTmaBoxRows, &bar);
+        }
+        mbar_wait(&bar, parity);
+        parity ^= 1u;
+        if (taper) {
+            const f2x wa = f2x_set(taper[t0], taper[t0 + 1]), wb = f2x_set(taper[t0 + 2], taper[t0 + 3]);
+            for (int c = tid; c < nx; c += nthr) { cpd v = smem[c]; v.x = vmul(v.x, wa); v.y = vmul(v.y, wb); smem[c] = v; }
+            __syncthreads();
+        }
+        fft_forward_stages_dual(smem, cp.pl, cp.tw, 1, cp.fstride, tid, nthr);
+        for (int slot = tid; slot < nact; slot += nthr) {
+            const int2 pp = slot_pos[slot];
+            const cpd z = smem[pp.x], z2 = smem[pp.y];
+            const cpd xa = dmake(vmul(vadd(z.x, z2.x), half), vmul(vsub(z.y, z2.y), half));
+            const cpd xb = dmake(vmul(vadd(z.y, z2.y), half), vmul(vsub(z2.x, z.x), half));
+            float4* o = reinterpret_cast<float4*>(w + (size_t)slot * ldw + t0);
+            o[0] = make_float4(f2x_lo(xa.x), f2x_lo(xa.y), f2x_hi(xa.x), f2x_hi(xa.y));
+            o[1] = make_float4(f2x_lo(xb.x), f2x_lo(xb.y), f2x_hi(xb.x), f2x_hi(xb.y));
+        }
+        __syncthreads();          // every thread is done reading the tile before the next TMA overwrites it
+    }
+}
+
+// inverse: kept rows -> smem, inverse stages, smem --TMA--> y (asynchronous store)
+template <int MAXT>
+static __global__ void __launch_bounds__(MAXT, 1)
+k_col_inv_tma(const __grid_constant__ CUtensorMap tmy, ColParams cp, const float2* __restrict__ w, size_t ldw,
+              const int2* __restrict__ slot_pos, int nact, int ntiles) {
+    cpd* smem = reinterpret_cast<cpd*>(d4w_dyn_smem);
+    const int tid = threadIdx.x, nthr = blockDim.x, nx = cp.nx;
+    const int nbox = (nx + kTmaBoxRows - 1) / kTmaBoxRows;
+    const cpd zero = dmake(vbc(0.f), vbc(0.f));
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int t0 = tile * 4;
+        if (tid == 0) tma_store_wait_read();           // previous tile's store has finished READING smem
+        __syncthreads();
+        for (int i = tid; i < cp.fstride; i += nthr) smem[i] = zero;
+        __syncthreads();
+        for (int slot = tid; slot < nact; slot += nthr) {
+            const int2 pp = slot_pos[slot];
+            const float4* src = reinterpret_cast<const float4*>(w + (size_t)slot * ldw + t0);
+            const float4 u = src[0], v = src[1];
+            if (pp.x == pp.y) {
+                smem[pp.x] = dmake(f2x_set(u.x, u.z), f2x_set(v.x, v.z));
+            } else {
+                smem[pp.x] = dmake(f2x_set(u.x - v.y, u.z - v.w), f2x_set(u.y + v.x, u.w + v.z));
+                smem[pp.y] = dmake(f2x_set(u.x + v.y, u.z + v.w), f2x_set(v.x - u.y, v.z - u.w));
+            }
+        }
+        __syncthreads();
+        fft_inverse_stages_dual(smem, cp.pl, cp.tw, 1, cp.fstride, tid, nthr);
+        fence_async_smem();                            // generic-proxy writes visible to the async proxy
+        __syncthreads();
+        if (tid == 0) {
+            for (int b = 0; b < nbox; ++b) tma_store_2d(&tmy, t0, b * kTmaBoxRows, smem + b * kTmaBoxRows);
+            tma_store_commit();
+        }
+    }
+    if (tid == 0) tma_store_wait_all();
+}
+#endif  // __CUDACC__
 
 template <int T1, bool INV>
 static __global__ void __launch_bounds__(128)
