@@ -51,8 +51,15 @@ static bool make_tile_map(CUtensorMap* map, const float* base, int nx, int ns) {
     const cuuint64_t strides[1] = {(cuuint64_t)ns * sizeof(float)};
     const cuuint32_t box[2] = {4, (cuuint32_t)kTmaBoxRows};
     const cuuint32_t estr[2] = {1, 1};
+    // L2 promotion: one DRAM access brings a 128/256-byte line into L2, so the neighbouring tiles (other
+    // SMs, microseconds later) hit in L2 instead of opening the same DRAM page again for 32 bytes
+    static const int promo = env_int("D4W_TMA_L2PROMO", 3);
+    const CUtensorMapL2promotion l2 = promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+                                    : promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                    : promo == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                                                 : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
     return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+               CU_TENSOR_MAP_SWIZZLE_NONE, l2, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 struct d4w_fk_plan {

@@ -18,8 +18,8 @@ namespace d4w {
 struct f2x { unsigned long long v; };
 __device__ __forceinline__ f2x f2x_set(float a, float b) { f2x r; asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(a), "f"(b)); return r; }
 __device__ __forceinline__ f2x vbc(float s) { return f2x_set(s, s); }
-__device__ __forceinline__ float f2x_lo(f2x a) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v)); return lo; }
-__device__ __forceinline__ float f2x_hi(f2x a) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v)); return hi; }
+__device__ __forceinline__ float f2x_lo(f2x a) { return __uint_as_float((unsigned)(a.v & 0xffffffffull)); }
+__device__ __forceinline__ float f2x_hi(f2x a) { return __uint_as_float((unsigned)(a.v >> 32)); }
 __device__ __forceinline__ f2x vadd(f2x a, f2x b) { f2x r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
 __device__ __forceinline__ f2x vsub(f2x a, f2x b) { f2x r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
 __device__ __forceinline__ f2x vmul(f2x a, f2x b) { f2x r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }

@@ -21,7 +21,7 @@ DX, FS = 2.0419046878814697, 200.0
 
 def _build(name, tmp):
     exe = os.path.join(tmp, name)
-    r = subprocess.run([NVCC, "-std=c++17", "-O2", "--expt-relaxed-constexpr", "-Wno-deprecated-gpu-targets",
+    r = subprocess.run([NVCC, "-std=c++17", "-O2", "--expt-relaxed-constexpr", "-arch=sm_100a",
                         "-o", exe, os.path.join(EMUL, name + ".cu")], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr + r.stdout
     return exe
