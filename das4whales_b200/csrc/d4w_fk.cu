@@ -71,6 +71,7 @@ struct d4w_fk_plan {
     float2 *d_tw_col = nullptr, *d_tw_row = nullptr, *d_twT = nullptr;
     int *d_k2pos = nullptr, *d_pos2k = nullptr, *d_pos2k_row = nullptr;
     float* d_taper = nullptr;
+    unsigned long long* d_dbg = nullptr;      // 8 phase-cycle counters (D4W_FK_DEBUG=1)
     std::vector<int> h_k2pos;
     int col_threads = 256, row_threads = 256;
     size_t col_smem = 0, row_smem = 0;
@@ -128,6 +129,7 @@ extern "C" int d4w_fk_plan_create(d4w_fk_plan** out, int nx, int ns, int device)
     if (e == cudaSuccess) e = upload(&pl->d_k2pos, k2p);
     if (e == cudaSuccess) e = upload(&pl->d_pos2k_row, p2kr);
     if (e == cudaSuccess) e = upload(&pl->d_taper, tap);
+    if (e == cudaSuccess && env_int("D4W_FK_DEBUG", 0)) { e = cudaMalloc((void**)&pl->d_dbg, 64); if (e == cudaSuccess) e = cudaMemset(pl->d_dbg, 0, 64); }
     // the attribute is per-kernel global state: always raise it to the device maximum, never to a plan's own size
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_col_fwd<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_col_inv<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
@@ -157,8 +159,17 @@ extern "C" int d4w_fk_plan_destroy(d4w_fk_plan* pl) {
     if (!pl) return D4W_OK;
     DeviceGuard guard(pl->device);
     cudaFree(pl->d_tw_col); cudaFree(pl->d_tw_row); cudaFree(pl->d_twT);
-    cudaFree(pl->d_k2pos); cudaFree(pl->d_pos2k); cudaFree(pl->d_pos2k_row); cudaFree(pl->d_taper);
+    cudaFree(pl->d_k2pos); cudaFree(pl->d_pos2k); cudaFree(pl->d_pos2k_row); cudaFree(pl->d_taper); cudaFree(pl->d_dbg);
     delete pl;
+    return D4W_OK;
+}
+
+extern "C" int d4w_fk_debug_phases(d4w_fk_plan* pl, unsigned long long* host8) {
+    if (!pl || !host8) return fail(D4W_ERR_ARG, "d4w_fk_debug_phases: null argument");
+    if (!pl->d_dbg) return fail(D4W_ERR_ARG, "d4w_fk_debug_phases: create the plan with D4W_FK_DEBUG=1");
+    DeviceGuard guard(pl->device);
+    D4W_CUDA_TRY(cudaMemcpy(host8, pl->d_dbg, 64, cudaMemcpyDeviceToHost));
+    D4W_CUDA_TRY(cudaMemset(pl->d_dbg, 0, 64));
     return D4W_OK;
 }
 
@@ -354,7 +365,7 @@ extern "C" int d4w_fk_apply_pass_ex(d4w_fk_plan* pl, d4w_fk_mask* m, const float
                 if (make_tile_map(&tm, x, pl->nx, pl->ns)) {
                     const int grid = std::min(ntiles, pl->num_sms);
                     k_col_fwd_tma<512><<<grid, std::min(pl->col_threads, 512), pl->col_smem, stream>>>(tm, pl->col, w, ldw, m->d_slot_pos,
-                                                                                                   nact, tap, ntiles);
+                                                                                                   nact, tap, ntiles, pl->d_dbg);
                     D4W_CHECK_LAUNCH("k_col_fwd_tma");
                     return D4W_OK;
                 }
@@ -392,7 +403,7 @@ extern "C" int d4w_fk_apply_pass_ex(d4w_fk_plan* pl, d4w_fk_mask* m, const float
                 if (make_tile_map(&tm, y, pl->nx, pl->ns)) {
                     const int grid = std::min(ntiles, pl->num_sms);
                     k_col_inv_tma<512><<<grid, std::min(pl->col_threads, 512), pl->col_smem, stream>>>(tm, pl->col, w, ldw, m->d_slot_pos,
-                                                                                                   nact, ntiles);
+                                                                                                   nact, ntiles, pl->d_dbg);
                     D4W_CHECK_LAUNCH("k_col_inv_tma");
                     return D4W_OK;
                 }

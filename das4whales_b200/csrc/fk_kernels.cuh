@@ -498,9 +498,11 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 template <int MAXT>
 static __global__ void __launch_bounds__(MAXT, 1)
 k_col_fwd_tma(const __grid_constant__ CUtensorMap tmx, ColParams cp, float2* __restrict__ w, size_t ldw,
-              const int2* __restrict__ slot_pos, int nact, const float* __restrict__ taper, int ntiles) {
+              const int2* __restrict__ slot_pos, int nact, const float* __restrict__ taper, int ntiles,
+              unsigned long long* __restrict__ dbg) {
     cpd* smem = reinterpret_cast<cpd*>(d4w_dyn_smem);
     __shared__ __align__(8) unsigned long long bar;
+    long long c_load = 0, c_fft = 0, c_out = 0, tc = 0;
     const int tid = threadIdx.x, nthr = blockDim.x, nx = cp.nx, ns = cp.ns;
     const int nbox = (nx + kTmaBoxRows - 1) / kTmaBoxRows;
     if (tid == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -509,18 +511,21 @@ k_col_fwd_tma(const __grid_constant__ CUtensorMap tmx, ColParams cp, float2* __r
     const f2x half = vbc(0.5f);
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int t0 = tile * 4;
+        if (dbg && tid == 0) tc = clock64();
         if (tid == 0) {
             mbar_expect_tx(&bar, (unsigned)(nbox * kTmaBoxRows * 16));
             for (int b = 0; b < nbox; ++b) tma_load_2d(smem + b * kTmaBoxRows, &tmx, t0, b * kTmaBoxRows, &bar);
         }
         mbar_wait(&bar, parity);
         parity ^= 1u;
+        if (dbg && tid == 0) { const long long t = clock64(); c_load += t - tc; tc = t; }
         if (taper) {
             const f2x wa = f2x_set(taper[t0], taper[t0 + 1]), wb = f2x_set(taper[t0 + 2], taper[t0 + 3]);
             for (int c = tid; c < nx; c += nthr) { cpd v = smem[c]; v.x = vmul(v.x, wa); v.y = vmul(v.y, wb); smem[c] = v; }
             __syncthreads();
         }
         fft_forward_stages_dual(smem, cp.pl, cp.tw, 1, cp.fstride, tid, nthr);
+        if (dbg && tid == 0) { const long long t = clock64(); c_fft += t - tc; tc = t; }
         for (int slot = tid; slot < nact; slot += nthr) {
             const int2 pp = slot_pos[slot];
             const cpd z = smem[pp.x], z2 = smem[pp.y];
@@ -531,6 +536,11 @@ k_col_fwd_tma(const __grid_constant__ CUtensorMap tmx, ColParams cp, float2* __r
             o[1] = make_float4(f2x_lo(xb.x), f2x_lo(xb.y), f2x_hi(xb.x), f2x_hi(xb.y));
         }
         __syncthreads();          // every thread is done reading the tile before the next TMA overwrites it
+        if (dbg && tid == 0) { const long long t = clock64(); c_out += t - tc; tc = t; }
+    }
+    if (dbg && tid == 0) {
+        atomicAdd(dbg + 0, (unsigned long long)c_load); atomicAdd(dbg + 1, (unsigned long long)c_fft);
+        atomicAdd(dbg + 2, (unsigned long long)c_out);
     }
 }
 
@@ -538,15 +548,18 @@ k_col_fwd_tma(const __grid_constant__ CUtensorMap tmx, ColParams cp, float2* __r
 template <int MAXT>
 static __global__ void __launch_bounds__(MAXT, 1)
 k_col_inv_tma(const __grid_constant__ CUtensorMap tmy, ColParams cp, const float2* __restrict__ w, size_t ldw,
-              const int2* __restrict__ slot_pos, int nact, int ntiles) {
+              const int2* __restrict__ slot_pos, int nact, int ntiles, unsigned long long* __restrict__ dbg) {
     cpd* smem = reinterpret_cast<cpd*>(d4w_dyn_smem);
     const int tid = threadIdx.x, nthr = blockDim.x, nx = cp.nx;
     const int nbox = (nx + kTmaBoxRows - 1) / kTmaBoxRows;
     const cpd zero = dmake(vbc(0.f), vbc(0.f));
+    long long c_wait = 0, c_fill = 0, c_fft = 0, c_st = 0, tc = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int t0 = tile * 4;
+        if (dbg && tid == 0) tc = clock64();
         if (tid == 0) tma_store_wait_read();           // previous tile's store has finished READING smem
         __syncthreads();
+        if (dbg && tid == 0) { const long long t = clock64(); c_wait += t - tc; tc = t; }
         for (int i = tid; i < cp.fstride; i += nthr) smem[i] = zero;
         __syncthreads();
         for (int slot = tid; slot < nact; slot += nthr) {
@@ -561,15 +574,22 @@ k_col_inv_tma(const __grid_constant__ CUtensorMap tmy, ColParams cp, const float
             }
         }
         __syncthreads();
+        if (dbg && tid == 0) { const long long t = clock64(); c_fill += t - tc; tc = t; }
         fft_inverse_stages_dual(smem, cp.pl, cp.tw, 1, cp.fstride, tid, nthr);
         fence_async_smem();                            // generic-proxy writes visible to the async proxy
         __syncthreads();
+        if (dbg && tid == 0) { const long long t = clock64(); c_fft += t - tc; tc = t; }
         if (tid == 0) {
             for (int b = 0; b < nbox; ++b) tma_store_2d(&tmy, t0, b * kTmaBoxRows, smem + b * kTmaBoxRows);
             tma_store_commit();
         }
+        if (dbg && tid == 0) { const long long t = clock64(); c_st += t - tc; tc = t; }
     }
     if (tid == 0) tma_store_wait_all();
+    if (dbg && tid == 0) {
+        atomicAdd(dbg + 4, (unsigned long long)c_wait); atomicAdd(dbg + 5, (unsigned long long)c_fill);
+        atomicAdd(dbg + 6, (unsigned long long)c_fft); atomicAdd(dbg + 7, (unsigned long long)c_st);
+    }
 }
 #endif  // __CUDACC__
 

@@ -47,6 +47,10 @@ int d4w_fk_plan_destroy(d4w_fk_plan* plan);
 /* describe the plan: info[0]=T1 (row split), [1]=T2, [2]=column tile width in samples,
  * [3]=column stages, [4]=row stages, [5]=column threads, [6]=row threads, [7]=reserved */
 int d4w_fk_plan_info(const d4w_fk_plan* plan, int* info8);
+/* profiling aid (plan created with env D4W_FK_DEBUG=1): summed SM cycles per phase of the TMA column
+ * kernels since the last call -- [0..2] forward: load wait, FFT, untangle+store; [4..7] inverse: store
+ * drain, fill, FFT, store issue.  Synchronises the device. */
+int d4w_fk_debug_phases(d4w_fk_plan* plan, unsigned long long* host8);
 
 /* Mask descriptors.  All masks are defined exactly as the reference defines them, in the
  * fftshift-ed (k, f) layout; the library folds M_sym = (M[k,f] + M[-k,-f]) / 2 (what taking

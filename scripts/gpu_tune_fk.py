@@ -29,6 +29,15 @@ def one():
             ev[r][i + 1].record()
     torch.cuda.synchronize()
     ms = [sum(ev[r][i].elapsed_time(ev[r][i + 1]) for r in range(reps)) / reps for i in range(5)]
+    if os.environ.get("D4W_FK_DEBUG"):
+        from das4whales_b200 import _lib
+        buf = _lib.ffi.new("unsigned long long[8]")
+        _lib.lib().d4w_fk_debug_phases(flt.plan.ptr, buf)      # reset
+        flt(x, out=y); torch.cuda.synchronize()
+        _lib.check(_lib.lib().d4w_fk_debug_phases(flt.plan.ptr, buf), "dbg")
+        nsm = 148
+        print("phase Mcycles per SM (one apply): fwd load/fft/out =", [round(buf[i] / nsm / 1e6, 3) for i in range(3)],
+              " inv drain/fill/fft/store =", [round(buf[i] / nsm / 1e6, 3) for i in range(4, 8)])
     print(json.dumps({"ms": [round(m, 3) for m in ms], "total": round(sum(ms), 3), "err": err,
                       "t1": flt.plan.t1, "t2": flt.plan.t2, "tile": flt.plan.tile}))
 
