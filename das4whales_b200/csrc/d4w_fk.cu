@@ -364,8 +364,10 @@ extern "C" int d4w_fk_apply_pass_ex(d4w_fk_plan* pl, d4w_fk_mask* m, const float
                 CUtensorMap tm;
                 if (make_tile_map(&tm, x, pl->nx, pl->ns)) {
                     const int grid = std::min(ntiles, pl->num_sms);
-                    k_col_fwd_tma<512><<<grid, std::min(pl->col_threads, 512), pl->col_smem, stream>>>(tm, pl->col, w, ldw, m->d_slot_pos,
-                                                                                                   nact, tap, ntiles, pl->d_dbg);
+                    const int nbox = (pl->nx + kTmaBoxRows - 1) / kTmaBoxRows;
+                    const int tma_boxes = std::min(nbox, std::max(0, nbox * env_int("D4W_TMA_LOAD_PCT", 57) / 100));
+                    k_col_fwd_tma<512><<<grid, std::min(pl->col_threads, 512), pl->col_smem, stream>>>(tm, pl->col, x, w, ldw, m->d_slot_pos,
+                                                                                                   nact, tap, ntiles, tma_boxes, pl->d_dbg);
                     D4W_CHECK_LAUNCH("k_col_fwd_tma");
                     return D4W_OK;
                 }
@@ -402,8 +404,10 @@ extern "C" int d4w_fk_apply_pass_ex(d4w_fk_plan* pl, d4w_fk_mask* m, const float
                 CUtensorMap tm;
                 if (make_tile_map(&tm, y, pl->nx, pl->ns)) {
                     const int grid = std::min(ntiles, pl->num_sms);
+                    const int nbox = (pl->nx + kTmaBoxRows - 1) / kTmaBoxRows;
+                    const int tma_boxes = std::min(nbox, std::max(0, nbox * env_int("D4W_TMA_STORE_PCT", 57) / 100));
                     k_col_inv_tma<512><<<grid, std::min(pl->col_threads, 512), pl->col_smem, stream>>>(tm, pl->col, w, ldw, m->d_slot_pos,
-                                                                                                   nact, ntiles, pl->d_dbg);
+                                                                                                   nact, ntiles, y, tma_boxes, pl->d_dbg);
                     D4W_CHECK_LAUNCH("k_col_inv_tma");
                     return D4W_OK;
                 }

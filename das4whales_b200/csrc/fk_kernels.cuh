@@ -133,7 +133,7 @@ __host__ __device__ inline void body_mask_build(const MaskParams& mp, float* tab
 }
 
 // ------------------------------------------------------------------ async copy helpers
-#ifdef __CUDA_ARCH__
+#ifdef __CUDACC__
 __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc) : "memory");
@@ -407,8 +407,19 @@ __host__ __device__ inline void body_row_mid(const RowParams& rp, float2* __rest
                                              int tid, int nthr, float2* smem) {
     const int n = rp.t2;
     float2* g = w + (size_t)slot * ldw + (size_t)kt1 * n;
-    for (int i = tid; i < n; i += nthr) smem[i] = g[i];
-    D4W_SYNC();
+    bool staged = false;
+#ifdef __CUDA_ARCH__
+    if ((n & 1) == 0 && ((((size_t)slot * ldw + (size_t)kt1 * n) & 1) == 0)) {
+        for (int i = tid; i < n / 2; i += nthr) cp_async16(smem + 2 * i, g + 2 * i);     // whole tile in flight
+        cp_async_wait_all();
+        __syncthreads();
+        staged = true;
+    }
+#endif
+    if (!staged) {
+        for (int i = tid; i < n; i += nthr) smem[i] = g[i];
+        D4W_SYNC();
+    }
     fft_forward_stages(smem, rp.pl, rp.tw, 1, n, tid, nthr, 0, rp.pl.nstages);
     const float* m = tab + (size_t)slot * tab_slot_stride + (size_t)kt1 * n;
     for (int i = tid; i < n; i += nthr) { const float s = m[i]; float2 v = smem[i]; v.x *= s; v.y *= s; smem[i] = v; }
@@ -494,30 +505,42 @@ __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.b
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// forward: x --TMA--> smem, forward stages, untangle + pruned store (same math as body_col_fwd_dual)
+// forward: x --TMA + cp.async--> smem, forward stages, untangle + pruned store.
+// The tile's rows are split between the two copy engines (TMA boxes for the first tma_rows rows,
+// 16-byte cp.async for the rest) so their per-row request rates add up; the kept elements of the
+// finished tile are pulled into registers first, so the next tile's copy runs under the untangle.
+constexpr int kMaxOutPerThread = 3;
 template <int MAXT>
 static __global__ void __launch_bounds__(MAXT, 1)
-k_col_fwd_tma(const __grid_constant__ CUtensorMap tmx, ColParams cp, float2* __restrict__ w, size_t ldw,
-              const int2* __restrict__ slot_pos, int nact, const float* __restrict__ taper, int ntiles,
+k_col_fwd_tma(const __grid_constant__ CUtensorMap tmx, ColParams cp, const float* __restrict__ x, float2* __restrict__ w, size_t ldw,
+              const int2* __restrict__ slot_pos, int nact, const float* __restrict__ taper, int ntiles, int tma_boxes,
               unsigned long long* __restrict__ dbg) {
     cpd* smem = reinterpret_cast<cpd*>(d4w_dyn_smem);
     __shared__ __align__(8) unsigned long long bar;
     long long c_load = 0, c_fft = 0, c_out = 0, tc = 0;
     const int tid = threadIdx.x, nthr = blockDim.x, nx = cp.nx, ns = cp.ns;
-    const int nbox = (nx + kTmaBoxRows - 1) / kTmaBoxRows;
+    const int tma_rows = min(nx, tma_boxes * kTmaBoxRows);
+    const bool regs_ok = nact <= kMaxOutPerThread * nthr;
     if (tid == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     __syncthreads();
     unsigned parity = 0;
     const f2x half = vbc(0.5f);
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    auto issue_load = [&](int tile) {
+        const int t0 = tile * 4;
+        if (tid == 0 && tma_boxes > 0) {
+            mbar_expect_tx(&bar, (unsigned)(tma_boxes * kTmaBoxRows * 16));
+            for (int b = 0; b < tma_boxes; ++b) tma_load_2d(smem + b * kTmaBoxRows, &tmx, t0, b * kTmaBoxRows, &bar);
+        }
+        for (int c = tma_rows + tid; c < nx; c += nthr) cp_async16(smem + c, x + (size_t)c * ns + t0);
+    };
+    int tile = blockIdx.x;
+    if (tile < ntiles) issue_load(tile);
+    for (; tile < ntiles; tile += gridDim.x) {
         const int t0 = tile * 4;
         if (dbg && tid == 0) tc = clock64();
-        if (tid == 0) {
-            mbar_expect_tx(&bar, (unsigned)(nbox * kTmaBoxRows * 16));
-            for (int b = 0; b < nbox; ++b) tma_load_2d(smem + b * kTmaBoxRows, &tmx, t0, b * kTmaBoxRows, &bar);
-        }
-        mbar_wait(&bar, parity);
-        parity ^= 1u;
+        cp_async_wait_all();
+        if (tma_boxes > 0) { mbar_wait(&bar, parity); parity ^= 1u; }
+        __syncthreads();
         if (dbg && tid == 0) { const long long t = clock64(); c_load += t - tc; tc = t; }
         if (taper) {
             const f2x wa = f2x_set(taper[t0], taper[t0 + 1]), wb = f2x_set(taper[t0 + 2], taper[t0 + 3]);
@@ -526,16 +549,40 @@ k_col_fwd_tma(const __grid_constant__ CUtensorMap tmx, ColParams cp, float2* __r
         }
         fft_forward_stages_dual(smem, cp.pl, cp.tw, 1, cp.fstride, tid, nthr);
         if (dbg && tid == 0) { const long long t = clock64(); c_fft += t - tc; tc = t; }
-        for (int slot = tid; slot < nact; slot += nthr) {
-            const int2 pp = slot_pos[slot];
-            const cpd z = smem[pp.x], z2 = smem[pp.y];
-            const cpd xa = dmake(vmul(vadd(z.x, z2.x), half), vmul(vsub(z.y, z2.y), half));
-            const cpd xb = dmake(vmul(vadd(z.y, z2.y), half), vmul(vsub(z2.x, z.x), half));
-            float4* o = reinterpret_cast<float4*>(w + (size_t)slot * ldw + t0);
-            o[0] = make_float4(f2x_lo(xa.x), f2x_lo(xa.y), f2x_hi(xa.x), f2x_hi(xa.y));
-            o[1] = make_float4(f2x_lo(xb.x), f2x_lo(xb.y), f2x_hi(xb.x), f2x_hi(xb.y));
+        const int next = tile + gridDim.x;
+        if (regs_ok) {
+            cpd z[kMaxOutPerThread], z2[kMaxOutPerThread];
+#pragma unroll
+            for (int j = 0; j < kMaxOutPerThread; ++j) {
+                const int slot = tid + j * nthr;
+                if (slot < nact) { const int2 pp = slot_pos[slot]; z[j] = smem[pp.x]; z2[j] = smem[pp.y]; }
+            }
+            __syncthreads();                       // tile fully consumed -> its buffer is free
+            if (next < ntiles) issue_load(next);   // next tile streams in while we untangle from registers
+#pragma unroll
+            for (int j = 0; j < kMaxOutPerThread; ++j) {
+                const int slot = tid + j * nthr;
+                if (slot < nact) {
+                    const cpd xa = dmake(vmul(vadd(z[j].x, z2[j].x), half), vmul(vsub(z[j].y, z2[j].y), half));
+                    const cpd xb = dmake(vmul(vadd(z[j].y, z2[j].y), half), vmul(vsub(z2[j].x, z[j].x), half));
+                    float4* o = reinterpret_cast<float4*>(w + (size_t)slot * ldw + t0);
+                    o[0] = make_float4(f2x_lo(xa.x), f2x_lo(xa.y), f2x_hi(xa.x), f2x_hi(xa.y));
+                    o[1] = make_float4(f2x_lo(xb.x), f2x_lo(xb.y), f2x_hi(xb.x), f2x_hi(xb.y));
+                }
+            }
+        } else {
+            for (int slot = tid; slot < nact; slot += nthr) {
+                const int2 pp = slot_pos[slot];
+                const cpd z = smem[pp.x], z2 = smem[pp.y];
+                const cpd xa = dmake(vmul(vadd(z.x, z2.x), half), vmul(vsub(z.y, z2.y), half));
+                const cpd xb = dmake(vmul(vadd(z.y, z2.y), half), vmul(vsub(z2.x, z.x), half));
+                float4* o = reinterpret_cast<float4*>(w + (size_t)slot * ldw + t0);
+                o[0] = make_float4(f2x_lo(xa.x), f2x_lo(xa.y), f2x_hi(xa.x), f2x_hi(xa.y));
+                o[1] = make_float4(f2x_lo(xb.x), f2x_lo(xb.y), f2x_hi(xb.x), f2x_hi(xb.y));
+            }
+            __syncthreads();
+            if (next < ntiles) issue_load(next);
         }
-        __syncthreads();          // every thread is done reading the tile before the next TMA overwrites it
         if (dbg && tid == 0) { const long long t = clock64(); c_out += t - tc; tc = t; }
     }
     if (dbg && tid == 0) {
@@ -548,10 +595,12 @@ k_col_fwd_tma(const __grid_constant__ CUtensorMap tmx, ColParams cp, float2* __r
 template <int MAXT>
 static __global__ void __launch_bounds__(MAXT, 1)
 k_col_inv_tma(const __grid_constant__ CUtensorMap tmy, ColParams cp, const float2* __restrict__ w, size_t ldw,
-              const int2* __restrict__ slot_pos, int nact, int ntiles, unsigned long long* __restrict__ dbg) {
+              const int2* __restrict__ slot_pos, int nact, int ntiles, float* __restrict__ y, int tma_boxes,
+              unsigned long long* __restrict__ dbg) {
     cpd* smem = reinterpret_cast<cpd*>(d4w_dyn_smem);
-    const int tid = threadIdx.x, nthr = blockDim.x, nx = cp.nx;
-    const int nbox = (nx + kTmaBoxRows - 1) / kTmaBoxRows;
+    const int tid = threadIdx.x, nthr = blockDim.x, nx = cp.nx, ns = cp.ns;
+    const int nbox = tma_boxes;
+    const int tma_rows = min(nx, tma_boxes * kTmaBoxRows);
     const cpd zero = dmake(vbc(0.f), vbc(0.f));
     long long c_wait = 0, c_fill = 0, c_fft = 0, c_st = 0, tc = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -579,10 +628,13 @@ k_col_inv_tma(const __grid_constant__ CUtensorMap tmy, ColParams cp, const float
         fence_async_smem();                            // generic-proxy writes visible to the async proxy
         __syncthreads();
         if (dbg && tid == 0) { const long long t = clock64(); c_fft += t - tc; tc = t; }
-        if (tid == 0) {
+        if (tid == 0 && nbox > 0) {
             for (int b = 0; b < nbox; ++b) tma_store_2d(&tmy, t0, b * kTmaBoxRows, smem + b * kTmaBoxRows);
             tma_store_commit();
         }
+        // the remaining rows leave through the LSU at the same time (16-byte row stores)
+        for (int c = tma_rows + tid; c < nx; c += nthr)
+            *reinterpret_cast<float4*>(y + (size_t)c * ns + t0) = *reinterpret_cast<const float4*>(smem + c);
         if (dbg && tid == 0) { const long long t = clock64(); c_st += t - tc; tc = t; }
     }
     if (tid == 0) tma_store_wait_all();
