@@ -122,28 +122,60 @@ template <bool INV> struct DFTD<5, INV> {
     }
 };
 
+// Composite radix, IN PLACE with permuted output: R = R1*R2 (both factors are base radices for every
+// radix we use), input v[n] natural; on return X[m] sits at v[outpos<R>(m)].  No second register
+// array: the R2 length-R1 column DFTs, the internal twiddles and the R1 length-R2 row DFTs all
+// overwrite v, and the transposition is absorbed into the caller's store indices.
+template <int R> constexpr int outpos(int m) {
+    constexpr int R1 = pick_r1<R>();
+    constexpr int R2 = R / R1;
+    return (R1 == R) ? m : R2 * (m % R1) + (m / R1);
+}
+
 template <int R, bool INV> struct DFTD {
     static constexpr int R1 = pick_r1<R>();
     static constexpr int R2 = R / R1;
     static_assert(R1 != R, "prime radix > 5 is handled by the generic stage");
+    static_assert(pick_r1<R2>() == R2 || R2 == 4, "two-level composites only");
     static D4W_HD void run(cpd (&v)[R]) {
-        cpd t[R];
         static_for<R2>([&](auto n2c) {
             constexpr int n2 = decltype(n2c)::value;
             cpd a[R1];
             static_for<R1>([&](auto n1c) { constexpr int n1 = decltype(n1c)::value; a[n1] = v[R2 * n1 + n2]; });
             DFTD<R1, INV>::run(a);
-            static_for<R1>([&](auto k1c) { constexpr int k1 = decltype(k1c)::value; t[n2 * R1 + k1] = dmul_tw<R, n2 * k1, INV>(a[k1]); });
+            static_for<R1>([&](auto k1c) { constexpr int k1 = decltype(k1c)::value; v[R2 * k1 + n2] = dmul_tw<R, n2 * k1, INV>(a[k1]); });
         });
         static_for<R1>([&](auto k1c) {
             constexpr int k1 = decltype(k1c)::value;
             cpd b[R2];
-            static_for<R2>([&](auto n2c) { constexpr int n2 = decltype(n2c)::value; b[n2] = t[n2 * R1 + k1]; });
+            static_for<R2>([&](auto n2c) { constexpr int n2 = decltype(n2c)::value; b[n2] = v[R2 * k1 + n2]; });
             DFTD<R2, INV>::run(b);
-            static_for<R2>([&](auto k2c) { constexpr int k2 = decltype(k2c)::value; v[k1 + R1 * k2] = b[k2]; });
+            static_for<R2>([&](auto k2c) { constexpr int k2 = decltype(k2c)::value; v[R2 * k1 + k2] = b[k2]; });
         });
     }
 };
+
+// v[pos(m)] *= w^m (or conj) for m = 1..R-1 with w^m = (w^B)^a * w^j, m = B*a + j: only B + 2 complex
+// registers of twiddle state, product depth <= 2 after the short chains (error ~ 5e-7).
+template <int R, bool CONJ, bool PERM> D4W_HD void apply_stage_twiddles(cpd (&v)[R], float2 w) {
+    constexpr int B = 5;
+    float2 bj[B];
+    bj[0] = make_float2(1.f, 0.f);
+    bj[1] = w;
+    static_for<B>([&](auto jc) { constexpr int j = decltype(jc)::value; if constexpr (j >= 2) bj[j] = cmul(bj[j / 2], bj[j - j / 2]); });
+    const float2 wB = cmul(bj[B / 2], bj[B - B / 2]);
+    float2 g = make_float2(1.f, 0.f);
+    static_for<R>([&](auto mc) {
+        constexpr int m = decltype(mc)::value;
+        if constexpr (m > 0) {
+            constexpr int a = m / B, j = m % B;
+            if constexpr (j == 0) g = (a == 1) ? wB : cmul(g, wB);
+            const float2 t = (a == 0) ? bj[j] : (j == 0 ? g : cmul(g, bj[j]));
+            constexpr int pos = PERM ? outpos<R>(m) : m;
+            v[pos] = CONJ ? dmulc_s(v[pos], t) : dmul_s(v[pos], t);
+        }
+    });
+}
 
 // ---------------------------------------------------------------- in-place smem stages on cpd elements
 template <int R, bool INV>
@@ -162,21 +194,13 @@ __host__ __device__ void stage_dual(cpd* __restrict__ s, const float2* __restric
         cpd v[R];
         static_for<R>([&](auto qc) { constexpr int q = decltype(qc)::value; v[q] = base[q * L]; });
         if constexpr (!INV) {
-            DFTD<R, false>::run(v);
-            if (L > 1) {
-                float2 p[R];
-                twiddle_powers<R>(tw[twstep * n], p);
-                static_for<R>([&](auto mc) { constexpr int m = decltype(mc)::value; if constexpr (m > 0) v[m] = dmul_s(v[m], p[m]); });
-            }
+            DFTD<R, false>::run(v);                                   // X[m] at v[outpos(m)]
+            if (L > 1) apply_stage_twiddles<R, false, true>(v, tw[twstep * n]);
         } else {
-            if (L > 1) {
-                float2 p[R];
-                twiddle_powers<R>(tw[twstep * n], p);
-                static_for<R>([&](auto mc) { constexpr int m = decltype(mc)::value; if constexpr (m > 0) v[m] = dmulc_s(v[m], p[m]); });
-            }
+            if (L > 1) apply_stage_twiddles<R, true, false>(v, tw[twstep * n]);
             DFTD<R, true>::run(v);
         }
-        static_for<R>([&](auto qc) { constexpr int q = decltype(qc)::value; base[q * L] = v[q]; });
+        static_for<R>([&](auto qc) { constexpr int q = decltype(qc)::value; base[q * L] = v[outpos<R>(q)]; });
     }
 }
 
@@ -247,12 +271,13 @@ __host__ __device__ inline void stage_dispatch_dual(cpd* s, const float2* tw, in
     switch (r) {
 #define D4W_CASE(RR) case RR: stage_dual<RR, INV>(s, tw, n_total, ns, nfft, fstride, tid, nthr); break;
         D4W_CASE(2) D4W_CASE(3) D4W_CASE(4) D4W_CASE(5) D4W_CASE(6) D4W_CASE(8) D4W_CASE(10) D4W_CASE(12) D4W_CASE(15) D4W_CASE(16)
+        D4W_CASE(20) D4W_CASE(25)
 #undef D4W_CASE
         default: stage_generic_dual<INV>(s, tw, n_total, ns, r, nfft, fstride, tid, nthr); break;
     }
 }
 
-constexpr int kDualMaxRadix = 16;     // radix 20 / 25 need > 255 registers with two lanes
+constexpr int kDualMaxRadix = 25;     // radix > 16 needs ~150-170 registers -> 256-thread kernels
 
 __host__ __device__ inline void fft_forward_stages_dual(cpd* s, const FftPlan& pl, const float2* tw, int nfft, int fstride,
                                                         int tid, int nthr) {

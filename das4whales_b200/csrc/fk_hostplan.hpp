@@ -10,7 +10,7 @@ namespace d4w {
 struct FkHostPlan {
     int nx = 0, ns = 0;
     int t1 = 1, t2 = 0, nc = 1, nc_shift = 0, fstride = 0, aligned = 0;
-    int dual = 0, npair = 0, npair_shift = 0, aligned16 = 0, tma = 0;
+    int dual = 0, npair = 0, npair_shift = 0, aligned16 = 0, tma = 0, col_max_radix = 0;
     FftPlan colpl{}, rowpl{};
     std::vector<float2> tw_col, tw_row, twT;
     std::vector<int> pos2k, k2pos, pos2k_row;
@@ -75,7 +75,7 @@ inline int build_fk_hostplan(int nx, int ns, size_t smem_cap, FkHostPlan& hp, st
     hp.tma = (hp.dual && hp.npair == 1 && hp.aligned16 && env_int("D4W_COL_TMA", 1) &&
               (size_t)((nx + 255) / 256 * 256) * 16 <= smem_cap - 1024) ? 1 : 0;
     if (hp.tma) { hp.fstride = (nx + 255) / 256 * 256; hp.col_smem = (size_t)hp.fstride * 16; }
-    if (!make_plan(nx, hp.dual ? std::min(col_maxr, 16) : col_maxr, hp.colpl, e2)) { err = "channel axis: " + e2; return 1; }
+    if (!make_plan(nx, hp.dual ? std::min(col_maxr, env_int("D4W_DUAL_MAX_RADIX", 25)) : col_maxr, hp.colpl, e2)) { err = "channel axis: " + e2; return 1; }
 
     int t1 = 0;
     const int forced_t1 = env_int("D4W_T1", 0);
@@ -96,6 +96,7 @@ inline int build_fk_hostplan(int nx, int ns, size_t smem_cap, FkHostPlan& hp, st
               " has no supported split (needs ns = T1*T2 with T1 <= 25, T2 <= 10240 and prime factors <= 61)";
         return 1;
     }
+    for (int st = 0; st < hp.colpl.nstages; ++st) hp.col_max_radix = std::max(hp.col_max_radix, hp.colpl.radix[st]);
     hp.t1 = t1; hp.t2 = ns / t1;
     hp.row_smem = (size_t)hp.t2 * sizeof(float2);
     hp.tw_col = make_twiddles(nx);

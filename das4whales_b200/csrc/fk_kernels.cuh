@@ -509,7 +509,7 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 // The tile's rows are split between the two copy engines (TMA boxes for the first tma_rows rows,
 // 16-byte cp.async for the rest) so their per-row request rates add up; the kept elements of the
 // finished tile are pulled into registers first, so the next tile's copy runs under the untangle.
-constexpr int kMaxOutPerThread = 3;
+constexpr int kMaxOutPerThread = 6;
 template <int MAXT>
 static __global__ void __launch_bounds__(MAXT, 1)
 k_col_fwd_tma(const __grid_constant__ CUtensorMap tmx, ColParams cp, const float* __restrict__ x, float2* __restrict__ w, size_t ldw,
