@@ -603,23 +603,60 @@ k_col_inv_tma(const __grid_constant__ CUtensorMap tmy, ColParams cp, const float
     const int tma_rows = min(nx, tma_boxes * kTmaBoxRows);
     const cpd zero = dmake(vbc(0.f), vbc(0.f));
     long long c_wait = 0, c_fill = 0, c_fft = 0, c_st = 0, tc = 0;
+    // the slots a thread scatters are the same for every tile: keep their positions in registers
+    const bool regs_ok = nact <= kMaxOutPerThread * nthr;
+    int2 ppr[kMaxOutPerThread];
+#pragma unroll
+    for (int j = 0; j < kMaxOutPerThread; ++j) {
+        const int slot = tid + j * nthr;
+        ppr[j] = (regs_ok && slot < nact) ? slot_pos[slot] : make_int2(0, 0);
+    }
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int t0 = tile * 4;
         if (dbg && tid == 0) tc = clock64();
+        // all kept-row loads of this tile go out first; their DRAM latency hides under the drain + clear
+        float4 ru[kMaxOutPerThread], rv[kMaxOutPerThread];
+        if (regs_ok) {
+#pragma unroll
+            for (int j = 0; j < kMaxOutPerThread; ++j) {
+                const int slot = tid + j * nthr;
+                if (slot < nact) {
+                    const float4* src = reinterpret_cast<const float4*>(w + (size_t)slot * ldw + t0);
+                    ru[j] = src[0]; rv[j] = src[1];
+                }
+            }
+        }
         if (tid == 0) tma_store_wait_read();           // previous tile's store has finished READING smem
         __syncthreads();
         if (dbg && tid == 0) { const long long t = clock64(); c_wait += t - tc; tc = t; }
         for (int i = tid; i < cp.fstride; i += nthr) smem[i] = zero;
         __syncthreads();
-        for (int slot = tid; slot < nact; slot += nthr) {
-            const int2 pp = slot_pos[slot];
-            const float4* src = reinterpret_cast<const float4*>(w + (size_t)slot * ldw + t0);
-            const float4 u = src[0], v = src[1];
-            if (pp.x == pp.y) {
-                smem[pp.x] = dmake(f2x_set(u.x, u.z), f2x_set(v.x, v.z));
-            } else {
-                smem[pp.x] = dmake(f2x_set(u.x - v.y, u.z - v.w), f2x_set(u.y + v.x, u.w + v.z));
-                smem[pp.y] = dmake(f2x_set(u.x + v.y, u.z + v.w), f2x_set(v.x - u.y, v.z - u.w));
+        if (regs_ok) {
+#pragma unroll
+            for (int j = 0; j < kMaxOutPerThread; ++j) {
+                const int slot = tid + j * nthr;
+                if (slot < nact) {
+                    const int2 pp = ppr[j];
+                    const float4 u = ru[j], v = rv[j];
+                    if (pp.x == pp.y) {
+                        smem[pp.x] = dmake(f2x_set(u.x, u.z), f2x_set(v.x, v.z));
+                    } else {
+                        smem[pp.x] = dmake(f2x_set(u.x - v.y, u.z - v.w), f2x_set(u.y + v.x, u.w + v.z));
+                        smem[pp.y] = dmake(f2x_set(u.x + v.y, u.z + v.w), f2x_set(v.x - u.y, v.z - u.w));
+                    }
+                }
+            }
+        } else {
+            for (int slot = tid; slot < nact; slot += nthr) {
+                const int2 pp = slot_pos[slot];
+                const float4* src = reinterpret_cast<const float4*>(w + (size_t)slot * ldw + t0);
+                const float4 u = src[0], v = src[1];
+                if (pp.x == pp.y) {
+                    smem[pp.x] = dmake(f2x_set(u.x, u.z), f2x_set(v.x, v.z));
+                } else {
+                    smem[pp.x] = dmake(f2x_set(u.x - v.y, u.z - v.w), f2x_set(u.y + v.x, u.w + v.z));
+                    smem[pp.y] = dmake(f2x_set(u.x + v.y, u.z + v.w), f2x_set(v.x - u.y, v.z - u.w));
+                }
             }
         }
         __syncthreads();
