@@ -29,6 +29,19 @@ METRIC = "DAS channels/sec through f-k filter"
 CPU_SAMPLE_NX = 250                 # bounded CPU sample: 250 channels x the full 120 000 samples
 
 
+NCU_TRAFFIC_STEP = 21.1e9        # bytes per step, see traffic_source
+NCU_TRAFFIC_P5 = 6.44e9          # k_col_inv_tma, ncu dram bytes per launch
+
+
+def dominant(pass_ms, peak):
+    """SURVEY 8(d) K3 (inverse pass back to real samples): 4 B read + 4 B written per (channel, sample)."""
+    ms = pass_ms[4]
+    alg = 8 * NX * NS
+    ach = alg / (ms * 1e-3) / 1e9
+    return {"name": "k_col_inv_tma (P5, C2R over channels)", "ms": round(ms, 4), "algorithmic_bytes": alg,
+            "achieved": round(ach, 1), "frac": round(ach / peak, 4), "traffic": NCU_TRAFFIC_P5}
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -246,7 +259,10 @@ def main():
                            "plan": {"t1": flt.plan.t1, "t2": flt.plan.t2, "col_tile_samples": flt.plan.tile}},
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                             "frac": round(achieved / peak, 4), "traffic": None,
+                             "frac": round(achieved / peak, 4), "traffic": NCU_TRAFFIC_STEP,
+                             "traffic_source": "ncu --set full dram__bytes_read+write per launch, profiles/r01c_fk_tma_radix25.txt "
+                                               "(P1 6.18 + P3 3.27 + P5 6.44 GB) + P2/P4 at their algorithmic 2.60 GB each",
+                             "dominant_kernel": dominant(pass_ms, peak),
                              "peak_source": peak_src,
                              "scope": "whole f-k filter = 5 kernels per step; achieved = 24 B/(channel*sample) algorithmic bytes "
                                       "(SURVEY 8d) / step time; actual_bytes per kernel below are lower because wavenumber rows "

@@ -115,7 +115,7 @@ extern "C" int d4w_fk_plan_create(d4w_fk_plan** out, int nx, int ns, int device)
     pl->col_threads = std::min(1024, std::max(32, env_int("D4W_COL_THREADS", 512) / 32 * 32));
     if (hp.dual && hp.col_max_radix > 16) pl->col_threads = std::min(pl->col_threads, 256);   // register budget of radix 20/25
     pl->t1 = hp.t1; pl->t2 = hp.t2;
-    pl->row.pl = hp.rowpl; pl->row.t1 = hp.t1; pl->row.t2 = hp.t2;
+    pl->row.pl = hp.rowpl; pl->row.t1 = hp.t1; pl->row.t2 = hp.t2; pl->row.dual = hp.row_dual;
     pl->row_smem = hp.row_smem;
     pl->row_threads = env_int("D4W_ROW_THREADS", 256);
     const auto &twc = hp.tw_col, &twr = hp.tw_row, &twT = hp.twT;
@@ -147,6 +147,7 @@ extern "C" int d4w_fk_plan_create(d4w_fk_plan** out, int nx, int ns, int device)
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_col_fwd<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_col_inv<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_row_mid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_row_mid_dual, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
     if (e != cudaSuccess) {
         std::string msg = std::string("d4w_fk_plan_create: ") + cudaGetErrorString(e);
         d4w_fk_plan_destroy(pl);
@@ -396,6 +397,13 @@ extern "C" int d4w_fk_apply_pass_ex(d4w_fk_plan* pl, d4w_fk_mask* m, const float
             return launch_row_split<false>(pl, w, slot_count, stream);
         case 3: {
             if (slot_count == 0) return D4W_OK;
+            if (pl->row.dual) {
+                dim3 grid(pl->t1, (slot_count + 1) / 2);
+                k_row_mid_dual<<<grid, env_int("D4W_ROW_DUAL_THREADS", 128), pl->row_smem, stream>>>(pl->row, w, ldw, m->d_table + (size_t)slot_begin * pl->ns,
+                                                                    (size_t)pl->ns, slot_count);
+                D4W_CHECK_LAUNCH("k_row_mid_dual");
+                return D4W_OK;
+            }
             dim3 grid(pl->t1, slot_count);
             k_row_mid<<<grid, pl->row_threads, pl->row_smem, stream>>>(pl->row, w, ldw, m->d_table + (size_t)slot_begin * pl->ns,
                                                                        (size_t)pl->ns);

@@ -117,7 +117,7 @@ extern "C" int d4w_row_plan_create(d4w_row_plan** out, int ns, int device) {
     cudaDeviceProp prop;
     D4W_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     FkHostPlan hp; std::string err;
-    if (build_fk_hostplan(1, ns, prop.sharedMemPerBlockOptin, hp, err)) return fail(D4W_ERR_UNSUPPORTED, err);
+    if (build_fk_hostplan(1, ns, prop.sharedMemPerBlockOptin, hp, err, /*allow_row_dual=*/false)) return fail(D4W_ERR_UNSUPPORTED, err);
     auto p = new d4w_row_plan();
     p->ns = ns; p->device = device; p->t1 = hp.t1; p->t2 = hp.t2; p->row_smem = hp.row_smem;
     p->row.pl = hp.rowpl; p->row.t1 = hp.t1; p->row.t2 = hp.t2;

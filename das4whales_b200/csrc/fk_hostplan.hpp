@@ -11,6 +11,7 @@ struct FkHostPlan {
     int nx = 0, ns = 0;
     int t1 = 1, t2 = 0, nc = 1, nc_shift = 0, fstride = 0, aligned = 0;
     int dual = 0, npair = 0, npair_shift = 0, aligned16 = 0, tma = 0, col_max_radix = 0;
+    int row_dual = 0;
     FftPlan colpl{}, rowpl{};
     std::vector<float2> tw_col, tw_row, twT;
     std::vector<int> pos2k, k2pos, pos2k_row;
@@ -46,7 +47,7 @@ inline const std::vector<int>& split_radices() {
 }
 
 // returns 0 on success; 1 = unsupported shape (err says why)
-inline int build_fk_hostplan(int nx, int ns, size_t smem_cap, FkHostPlan& hp, std::string& err) {
+inline int build_fk_hostplan(int nx, int ns, size_t smem_cap, FkHostPlan& hp, std::string& err, bool allow_row_dual = true) {
     hp.nx = nx; hp.ns = ns;
     const int col_maxr = env_int("D4W_COL_MAX_RADIX", 25);
     const int row_maxr = env_int("D4W_ROW_MAX_RADIX", 16);
@@ -77,28 +78,47 @@ inline int build_fk_hostplan(int nx, int ns, size_t smem_cap, FkHostPlan& hp, st
     if (hp.tma) { hp.fstride = (nx + 255) / 256 * 256; hp.col_smem = (size_t)hp.fstride * 16; }
     if (!make_plan(nx, hp.dual ? std::min(col_maxr, env_int("D4W_DUAL_MAX_RADIX", 25)) : col_maxr, hp.colpl, e2)) { err = "channel axis: " + e2; return 1; }
 
+    // time axis = T1 (registers) x T2 (shared memory).  Dual-lane row kernel (default): T2 <= 6144 keeps the
+    // 16-byte-element tile under 96 KB -> two CTAs per SM; scalar kernel: T2 <= 10240 (16384 when T1 == 1).
     int t1 = 0;
     const int forced_t1 = env_int("D4W_T1", 0);
+    hp.row_dual = (allow_row_dual && env_int("D4W_ROW_DUAL", 1)) ? 1 : 0;
+    const int row_maxr_eff = hp.row_dual ? std::max(row_maxr, 25) : row_maxr;
     for (int cand : split_radices()) {
         if (forced_t1 > 0 && cand != forced_t1) continue;
         if (ns % cand) continue;
         const int t2 = ns / cand;
-        const int limit = (cand == 1) ? 16384 : 10240;
+        const int limit = hp.row_dual ? 6144 : ((cand == 1) ? 16384 : 10240);
         if (forced_t1 == 0 && t2 > limit) continue;
-        if ((size_t)t2 * sizeof(float2) > smem_cap) continue;
+        if ((size_t)t2 * (hp.row_dual ? 16 : 8) > smem_cap - 1024) continue;
         FftPlan tmp;
-        if (!make_plan(t2, row_maxr, tmp, e2)) continue;
+        if (!make_plan(t2, row_maxr_eff, tmp, e2)) continue;
         t1 = cand; hp.rowpl = tmp;
         break;
     }
+    if (t1 == 0 && hp.row_dual) {     // no split fits the dual tile: fall back to the scalar row kernel's limits
+        hp.row_dual = 0;
+        for (int cand : split_radices()) {
+            if (forced_t1 > 0 && cand != forced_t1) continue;
+            if (ns % cand) continue;
+            const int t2 = ns / cand;
+            const int limit = (cand == 1) ? 16384 : 10240;
+            if (forced_t1 == 0 && t2 > limit) continue;
+            if ((size_t)t2 * sizeof(float2) > smem_cap) continue;
+            FftPlan tmp;
+            if (!make_plan(t2, row_maxr, tmp, e2)) continue;
+            t1 = cand; hp.rowpl = tmp;
+            break;
+        }
+    }
     if (t1 == 0) {
         err = "time axis length " + std::to_string(ns) +
-              " has no supported split (needs ns = T1*T2 with T1 <= 25, T2 <= 10240 and prime factors <= 61)";
+              " has no supported split (needs ns = T1*T2 with T1 <= 25, T2 <= 6144 (10240 scalar) and prime factors <= 61)";
         return 1;
     }
     for (int st = 0; st < hp.colpl.nstages; ++st) hp.col_max_radix = std::max(hp.col_max_radix, hp.colpl.radix[st]);
     hp.t1 = t1; hp.t2 = ns / t1;
-    hp.row_smem = (size_t)hp.t2 * sizeof(float2);
+    hp.row_smem = (size_t)hp.t2 * (hp.row_dual ? 16 : sizeof(float2));
     hp.tw_col = make_twiddles(nx);
     hp.tw_row = make_twiddles(hp.t2);
     hp.twT.resize((size_t)hp.t2);

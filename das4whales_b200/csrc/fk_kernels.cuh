@@ -41,6 +41,7 @@ struct RowParams {
     const float2* tw;      // W_T2^j
     const float2* twT;     // W_ns^j for j < T2 (split twiddles)
     int t1, t2;
+    int dual;              // 1: k_row_mid_dual (two kept rows per CTA as f32x2 lanes)
 };
 
 enum { MASK_FAN = 0, MASK_HYBRID_NINF = 1, MASK_DENSE = 2 };
@@ -428,6 +429,45 @@ __host__ __device__ inline void body_row_mid(const RowParams& rp, float2* __rest
     for (int i = tid; i < n; i += nthr) g[i] = smem[i];
 }
 
+
+// ------------------------------------------------------------------ P3 dual: two kept rows per CTA as f32x2 lanes
+// Rows slotA = 2*pair, slotB = slotA + 1 (same kt1 tile) are interleaved on the way into shared memory
+// ({reA, reB, imA, imB} per sample), share every butterfly / twiddle, and each lane is multiplied by its
+// own row of the mask table.  An odd trailing row runs with lane B = 0.
+__host__ __device__ inline void body_row_mid_dual(const RowParams& rp, float2* __restrict__ w, size_t ldw,
+                                                  const float* __restrict__ tab, size_t tab_slot_stride, int kt1, int pair,
+                                                  int nslots, int tid, int nthr, cpd* smem) {
+    const int n = rp.t2;
+    const int sa = 2 * pair, sb = sa + 1;
+    const bool has_b = sb < nslots;
+    float2* ga = w + (size_t)sa * ldw + (size_t)kt1 * n;
+    float2* gb = w + (size_t)(has_b ? sb : sa) * ldw + (size_t)kt1 * n;
+#pragma unroll 8
+    for (int i = tid; i < n; i += nthr) {
+        const float2 a = ga[i];
+        const float2 b = has_b ? gb[i] : make_float2(0.f, 0.f);
+        smem[i] = dmake(f2x_set(a.x, b.x), f2x_set(a.y, b.y));
+    }
+    D4W_SYNC();
+    fft_forward_stages_dual(smem, rp.pl, rp.tw, 1, n, tid, nthr);
+    const float* ma = tab + (size_t)sa * tab_slot_stride + (size_t)kt1 * n;
+    const float* mb = tab + (size_t)(has_b ? sb : sa) * tab_slot_stride + (size_t)kt1 * n;
+#pragma unroll 4
+    for (int i = tid; i < n; i += nthr) {
+        const f2x m = f2x_set(ma[i], mb[i]);
+        cpd v = smem[i];
+        v.x = vmul(v.x, m); v.y = vmul(v.y, m);
+        smem[i] = v;
+    }
+    D4W_SYNC();
+    fft_inverse_stages_dual(smem, rp.pl, rp.tw, 1, n, tid, nthr);
+    for (int i = tid; i < n; i += nthr) {
+        const cpd v = smem[i];
+        ga[i] = make_float2(f2x_lo(v.x), f2x_lo(v.y));
+        if (has_b) gb[i] = make_float2(f2x_hi(v.x), f2x_hi(v.y));
+    }
+}
+
 // ================================================================== __global__ wrappers
 #ifdef __CUDACC__
 extern __shared__ __align__(1024) float2 d4w_dyn_smem[];
@@ -692,6 +732,12 @@ k_row_split(float2* __restrict__ w, size_t ldw, int t2len, const float2* __restr
 static __global__ void __launch_bounds__(256, 2)
 k_row_mid(RowParams rp, float2* __restrict__ w, size_t ldw, const float* __restrict__ tab, size_t tab_slot_stride) {
     body_row_mid(rp, w, ldw, tab, tab_slot_stride, blockIdx.x, blockIdx.y, threadIdx.x, blockDim.x, d4w_dyn_smem);
+}
+
+static __global__ void __launch_bounds__(128, 2)     // radix-25 dual butterflies need ~190 registers: 2 x 128-thread CTAs per SM
+k_row_mid_dual(RowParams rp, float2* __restrict__ w, size_t ldw, const float* __restrict__ tab, size_t tab_slot_stride, int nslots) {
+    body_row_mid_dual(rp, w, ldw, tab, tab_slot_stride, blockIdx.x, blockIdx.y, nslots, threadIdx.x, blockDim.x,
+                      reinterpret_cast<cpd*>(d4w_dyn_smem));
 }
 
 static __global__ void k_mask_rowmax(MaskParams mp, unsigned int* rowmax, int fchunk) {

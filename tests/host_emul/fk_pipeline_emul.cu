@@ -46,7 +46,7 @@ int main(int argc, char** argv) {
     ColParams cp{}; cp.pl = hp.colpl; cp.tw = hp.tw_col.data(); cp.k2pos = hp.k2pos.data(); cp.pos2k = hp.pos2k.data();
     cp.nx = nx; cp.ns = ns; cp.nc = hp.nc; cp.nc_shift = hp.nc_shift; cp.fstride = hp.fstride; cp.aligned = hp.aligned;
     cp.dual = hp.dual; cp.npair = hp.npair; cp.npair_shift = hp.npair_shift; cp.aligned16 = hp.aligned16;
-    RowParams rp{}; rp.pl = hp.rowpl; rp.tw = hp.tw_row.data(); rp.twT = hp.twT.data(); rp.t1 = hp.t1; rp.t2 = hp.t2;
+    RowParams rp{}; rp.pl = hp.rowpl; rp.tw = hp.tw_row.data(); rp.twT = hp.twT.data(); rp.t1 = hp.t1; rp.t2 = hp.t2; rp.dual = hp.row_dual;
     MaskParams mp{}; mp.kind = kind; mp.nx = nx; mp.ns = ns; mp.kval = par[0]; mp.fval = par[1];
     mp.c0 = par[2]; mp.c1 = par[3]; mp.c2 = par[4]; mp.c3 = par[5];
     mp.h = H.data(); mp.col_lo = hdr[4]; mp.col_hi = hdr[5]; mp.dense = dense.data();
@@ -74,8 +74,14 @@ int main(int argc, char** argv) {
             else body_col_fwd(cp, x.data(), w.data(), ldw, slot_pos.data(), nact, taper ? hp.taper.data() : nullptr, b, 0, 1, smem.data());
         }
     if (hp.t1 > 1 && nact) split_dispatch(hp.t1, false, w.data(), ldw, hp.t2, hp.twT.data(), nact);
-    for (int s = 0; s < nact; ++s)
-        for (int k1 = 0; k1 < hp.t1; ++k1) body_row_mid(rp, w.data(), ldw, tab.data(), (size_t)ns, k1, s, 0, 1, smem.data());
+    if (hp.row_dual) {
+        for (int pr = 0; pr < (nact + 1) / 2; ++pr)
+            for (int k1 = 0; k1 < hp.t1; ++k1)
+                body_row_mid_dual(rp, w.data(), ldw, tab.data(), (size_t)ns, k1, pr, nact, 0, 1, reinterpret_cast<cpd*>(smem.data()));
+    } else {
+        for (int s = 0; s < nact; ++s)
+            for (int k1 = 0; k1 < hp.t1; ++k1) body_row_mid(rp, w.data(), ldw, tab.data(), (size_t)ns, k1, s, 0, 1, smem.data());
+    }
     if (hp.t1 > 1 && nact) split_dispatch(hp.t1, true, w.data(), ldw, hp.t2, hp.twT.data(), nact);
     for (int b = 0; b < ntiles; ++b) {
         if (hp.dual) body_col_inv_dual(cp, w.data(), ldw, slot_pos.data(), nact, y.data(), b, 0, 1, reinterpret_cast<cpd*>(smem.data()));
