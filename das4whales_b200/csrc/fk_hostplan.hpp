@@ -50,7 +50,7 @@ inline const std::vector<int>& split_radices() {
 inline int build_fk_hostplan(int nx, int ns, size_t smem_cap, FkHostPlan& hp, std::string& err, bool allow_row_dual = true) {
     hp.nx = nx; hp.ns = ns;
     const int col_maxr = env_int("D4W_COL_MAX_RADIX", 25);
-    const int row_maxr = env_int("D4W_ROW_MAX_RADIX", 16);
+    const int row_maxr = env_int("D4W_ROW_MAX_RADIX", 25);
     std::string e2;
     int nc = 8;
     const size_t col_budget = std::min<size_t>(smem_cap, 200 * 1024);
@@ -82,7 +82,7 @@ inline int build_fk_hostplan(int nx, int ns, size_t smem_cap, FkHostPlan& hp, st
     // 16-byte-element tile under 96 KB -> two CTAs per SM; scalar kernel: T2 <= 10240 (16384 when T1 == 1).
     int t1 = 0;
     const int forced_t1 = env_int("D4W_T1", 0);
-    hp.row_dual = (allow_row_dual && env_int("D4W_ROW_DUAL", 1)) ? 1 : 0;
+    hp.row_dual = (allow_row_dual && env_int("D4W_ROW_DUAL", 0)) ? 1 : 0;   // measured: scalar 16x25x25 + cp.async is faster (1.69 vs 1.91 ms)
     const int row_maxr_eff = hp.row_dual ? std::max(row_maxr, 25) : row_maxr;
     for (int cand : split_radices()) {
         if (forced_t1 > 0 && cand != forced_t1) continue;
