@@ -28,7 +28,7 @@ extern "C" int d4w_fft_plan_create(d4w_fft_plan** out, int n, int device) {
     auto p = new d4w_fft_plan();
     p->n = n; p->device = device; p->smem_cap = prop.sharedMemPerBlockOptin;
     std::string err;
-    if (!make_plan(n, env_int("D4W_BLOCK_MAX_RADIX", 16), p->pl, err)) { delete p; return fail(D4W_ERR_UNSUPPORTED, err); }
+    if (!make_plan(n, env_int("D4W_BLOCK_MAX_RADIX", 25), p->pl, err)) { delete p; return fail(D4W_ERR_UNSUPPORTED, err); }
     p->pos2k = make_pos2freq(p->pl);
     std::vector<int> k2pos((size_t)n);
     for (int i = 0; i < n; ++i) k2pos[p->pos2k[i]] = i;
@@ -94,7 +94,7 @@ extern "C" int d4w_xcorr(d4w_fft_plan* p, const float* x, int nx, int ns, int va
     if (smem + 1024 > p->smem_cap) return fail(D4W_ERR_UNSUPPORTED, "d4w_xcorr: block length too large for shared memory");
     D4W_CUDA_TRY(cudaFuncSetAttribute(k_xcorr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_cap - 1024));  // minus its static smem
     dim3 grid((xp.nseg + 1) / 2, nx);
-    k_xcorr<<<grid, 256, smem, (cudaStream_t)stream>>>(xp, x, (const float2*)dev_tabs, dev_stats, dev_segpre, dev_mu_over_m, out,
+    k_xcorr<<<grid, 128, smem, (cudaStream_t)stream>>>(xp, x, (const float2*)dev_tabs, dev_stats, dev_segpre, dev_mu_over_m, out,
                                                       (size_t)nx * ns);
     D4W_CHECK_LAUNCH("k_xcorr");
     return D4W_OK;

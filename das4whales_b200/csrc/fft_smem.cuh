@@ -41,9 +41,12 @@ __host__ __device__ void stage_inreg(float2* __restrict__ s, const float2* __res
     const int per = n_total / R;          // butterflies per transform
     const int twstep = n_total / ns;      // tab stride for W_Ns
     const int total = per * nfft;
+    // many small transforms (STFT frames): make the transform index the fast lane index so that, with an odd
+    // fstride, neighbouring lanes fall into different banks even in the short-stride last stages
+    const bool f_fast = nfft >= 16;
     for (int id = tid; id < total; id += nthr) {
-        const int f = id / per;
-        const int j = id - f * per;
+        const int f = f_fast ? id % nfft : id / per;
+        const int j = f_fast ? id / nfft : id - f * per;
         const int b = j / L;
         const int n = j - b * L;
         float2* base = s + (size_t)f * fstride + b * ns + n;

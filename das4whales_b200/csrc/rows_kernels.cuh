@@ -99,14 +99,14 @@ struct XcorrParams {
     int nb, valid, ntpl, ns, normalize, nseg;
 };
 
-static __global__ void __launch_bounds__(256, 2)
+static __global__ void __launch_bounds__(128, 4)
 k_xcorr(XcorrParams xp, const float* __restrict__ x, const float2* __restrict__ tabs, const double* __restrict__ stats,
         const double* __restrict__ segpre, const double* __restrict__ mu_over_m, float* __restrict__ out, size_t out_tpl_stride) {
     extern __shared__ float2 sm[];
     float2* S = sm;                   // spectrum of the segment pair
     float2* B = sm + xp.nb;           // work buffer for the inverse
     float2* P = sm + 2 * xp.nb;       // exclusive prefix sums of the normalised samples (valid entries)
-    __shared__ float2 s_wsum[8];
+    __shared__ float2 s_wsum[32];
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, wid = tid >> 5;
     const int row = blockIdx.y;
     const int seg_a = 2 * blockIdx.x, seg_b = seg_a + 1;
