@@ -113,7 +113,7 @@ extern "C" int d4w_fk_plan_create(d4w_fk_plan** out, int nx, int ns, int device)
     pl->col.dual = hp.dual; pl->col.npair = hp.npair; pl->col.npair_shift = hp.npair_shift; pl->col.aligned16 = hp.aligned16;
     pl->col_smem = hp.col_smem;
     pl->col_threads = std::min(1024, std::max(32, env_int("D4W_COL_THREADS", 512) / 32 * 32));
-    if (hp.dual && hp.col_max_radix > 16) pl->col_threads = std::min(pl->col_threads, 256);   // register budget of radix 20/25
+    if (hp.dual && hp.col_max_radix > 16) pl->col_threads = std::min(pl->col_threads, env_int("D4W_COL_THREADS_R25", 256));   // register budget of radix 20/25
     pl->t1 = hp.t1; pl->t2 = hp.t2;
     pl->row.pl = hp.rowpl; pl->row.t1 = hp.t1; pl->row.t2 = hp.t2; pl->row.dual = hp.row_dual;
     pl->row_smem = hp.row_smem;
@@ -142,6 +142,8 @@ extern "C" int d4w_fk_plan_create(d4w_fk_plan** out, int nx, int ns, int device)
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_col_inv_dual<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_col_fwd_tma<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap - 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_col_inv_tma<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap - 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_col_fwd_tma<416>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap - 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_col_inv_tma<416>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap - 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_col_fwd_tma<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap - 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_col_inv_tma<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap - 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_col_fwd<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
@@ -373,6 +375,9 @@ extern "C" int d4w_fk_apply_pass_ex(d4w_fk_plan* pl, d4w_fk_mask* m, const float
                     if (pl->col_threads <= 256)
                         k_col_fwd_tma<256><<<grid, pl->col_threads, pl->col_smem, stream>>>(tm, pl->col, x, w, ldw, m->d_slot_pos, nact, tap,
                                                                                             ntiles, tma_boxes, pl->d_dbg);
+                    else if (pl->col_threads <= 416)
+                        k_col_fwd_tma<416><<<grid, pl->col_threads, pl->col_smem, stream>>>(tm, pl->col, x, w, ldw, m->d_slot_pos, nact, tap,
+                                                                                            ntiles, tma_boxes, pl->d_dbg);
                     else
                         k_col_fwd_tma<512><<<grid, std::min(pl->col_threads, 512), pl->col_smem, stream>>>(
                             tm, pl->col, x, w, ldw, m->d_slot_pos, nact, tap, ntiles, tma_boxes, pl->d_dbg);
@@ -423,6 +428,9 @@ extern "C" int d4w_fk_apply_pass_ex(d4w_fk_plan* pl, d4w_fk_mask* m, const float
                     const int tma_boxes = std::min(nbox, std::max(0, nbox * env_int("D4W_TMA_STORE_PCT", 100) / 100));
                     if (pl->col_threads <= 256)
                         k_col_inv_tma<256><<<grid, pl->col_threads, pl->col_smem, stream>>>(tm, pl->col, w, ldw, m->d_slot_pos, nact, ntiles, y,
+                                                                                            tma_boxes, pl->d_dbg);
+                    else if (pl->col_threads <= 416)
+                        k_col_inv_tma<416><<<grid, pl->col_threads, pl->col_smem, stream>>>(tm, pl->col, w, ldw, m->d_slot_pos, nact, ntiles, y,
                                                                                             tma_boxes, pl->d_dbg);
                     else
                         k_col_inv_tma<512><<<grid, std::min(pl->col_threads, 512), pl->col_smem, stream>>>(

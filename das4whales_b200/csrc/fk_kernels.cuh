@@ -551,7 +551,7 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 // finished tile are pulled into registers first, so the next tile's copy runs under the untangle.
 constexpr int kMaxOutPerThread = 6;
 template <int MAXT>
-static __global__ void __launch_bounds__(MAXT, 1)
+static __global__ void __maxnreg__(MAXT <= 256 ? 255 : MAXT <= 416 ? 152 : 128)
 k_col_fwd_tma(const __grid_constant__ CUtensorMap tmx, ColParams cp, const float* __restrict__ x, float2* __restrict__ w, size_t ldw,
               const int2* __restrict__ slot_pos, int nact, const float* __restrict__ taper, int ntiles, int tma_boxes,
               unsigned long long* __restrict__ dbg) {
@@ -633,7 +633,7 @@ k_col_fwd_tma(const __grid_constant__ CUtensorMap tmx, ColParams cp, const float
 
 // inverse: kept rows -> smem, inverse stages, smem --TMA--> y (asynchronous store)
 template <int MAXT>
-static __global__ void __launch_bounds__(MAXT, 1)
+static __global__ void __maxnreg__(MAXT <= 256 ? 255 : MAXT <= 416 ? 152 : 128)
 k_col_inv_tma(const __grid_constant__ CUtensorMap tmy, ColParams cp, const float2* __restrict__ w, size_t ldw,
               const int2* __restrict__ slot_pos, int nact, int ntiles, float* __restrict__ y, int tma_boxes,
               unsigned long long* __restrict__ dbg) {
