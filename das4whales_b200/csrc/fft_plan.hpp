@@ -79,6 +79,25 @@ inline bool make_plan(int n, int max_radix, FftPlan& pl, std::string& err) {
     return true;
 }
 
+// explicit stage order "20,20,25" (tuning knob); returns false if it does not multiply to n
+inline bool make_plan_from_string(int n, const char* spec, FftPlan& pl) {
+    std::vector<int> order;
+    long long prod = 1;
+    for (const char* c = spec; *c;) {
+        int v = 0;
+        while (*c >= '0' && *c <= '9') { v = v * 10 + (*c - '0'); ++c; }
+        if (v < 2) return false;
+        order.push_back(v); prod *= v;
+        if (*c == ',' || *c == 'x') ++c; else if (*c) return false;
+    }
+    if (prod != n || (int)order.size() > kMaxStages) return false;
+    pl.n = n; pl.nstages = (int)order.size();
+    int len = n;
+    for (int s = 0; s < kMaxStages; ++s) { pl.radix[s] = 1; pl.sub[s] = 1; }
+    for (int s = 0; s < pl.nstages; ++s) { pl.radix[s] = order[s]; pl.sub[s] = len; len /= order[s]; }
+    return true;
+}
+
 inline std::vector<float2> make_twiddles(int n) {
     std::vector<float2> t((size_t)std::max(n, 1));
     const double two_pi = 6.283185307179586476925286766559;
