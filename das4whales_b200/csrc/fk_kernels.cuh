@@ -597,6 +597,9 @@ k_col_fwd_tma(const __grid_constant__ CUtensorMap tmx, ColParams cp, const float
                 const int slot = tid + j * nthr;
                 if (slot < nact) { const int2 pp = slot_pos[slot]; z[j] = smem[pp.x]; z2[j] = smem[pp.y]; }
             }
+            // the in-place FFT wrote this buffer through the generic proxy; order those writes (and our reads)
+            // before the async-proxy (TMA) writes of the next tile
+            fence_async_smem();
             __syncthreads();                       // tile fully consumed -> its buffer is free
             if (next < ntiles) issue_load(next);   // next tile streams in while we untangle from registers
 #pragma unroll
@@ -620,6 +623,7 @@ k_col_fwd_tma(const __grid_constant__ CUtensorMap tmx, ColParams cp, const float
                 o[0] = make_float4(f2x_lo(xa.x), f2x_lo(xa.y), f2x_hi(xa.x), f2x_hi(xa.y));
                 o[1] = make_float4(f2x_lo(xb.x), f2x_lo(xb.y), f2x_hi(xb.x), f2x_hi(xb.y));
             }
+            fence_async_smem();
             __syncthreads();
             if (next < ntiles) issue_load(next);
         }
@@ -666,7 +670,7 @@ k_col_inv_tma(const __grid_constant__ CUtensorMap tmy, ColParams cp, const float
                 }
             }
         }
-        if (tid == 0) tma_store_wait_read();           // previous tile's store has finished READING smem
+        if (tid == 0) { tma_store_wait_read(); fence_async_smem(); }   // previous tile's store has finished READING smem
         __syncthreads();
         if (dbg && tid == 0) { const long long t = clock64(); c_wait += t - tc; tc = t; }
         for (int i = tid; i < cp.fstride; i += nthr) smem[i] = zero;
