@@ -207,9 +207,28 @@ extern "C" int d4w_sosfiltfilt(const float* x, float* y, float* tmp, int nx, int
     sp.nsec = nsec; sp.pad = padlen; sp.ns = ns;
     cudaStream_t stream = (cudaStream_t)stream_v;
     const int blocks = (nx + 31) / 32;
-    k_sos_pass<1><<<blocks, 32, 0, stream>>>(sp, x, tmp, y, nx);
+    // time chunking with a warm-up chosen from the slowest pole: |p|^warm < 1e-9 (exact at fp32 precision)
+    double rmax = 0.0;
+    for (int s = 0; s < nsec; ++s) {
+        const double a1 = sp.a1[s], a2 = sp.a2[s];
+        const double disc = a1 * a1 - 4.0 * a2;
+        const double r = disc < 0 ? std::sqrt(std::fabs(a2)) : std::max(std::fabs((-a1 + std::sqrt(disc)) / 2), std::fabs((-a1 - std::sqrt(disc)) / 2));
+        rmax = std::max(rmax, r);
+    }
+    const int next = ns + 2 * padlen;
+    int chunk = 0, warm = 0;
+    if (env_int("D4W_IIR_CHUNKED", 1) && rmax > 0.0 && rmax < 0.9995) {
+        warm = (int)std::ceil(std::log(1e-9) / std::log(rmax)) + 32;
+        warm = (warm + 31) / 32 * 32;
+        chunk = std::max(4 * warm, 4096);
+        chunk = (chunk + 31) / 32 * 32;
+        if (next < 2 * chunk) chunk = 0;          // short signals: plain sequential recursion
+    }
+    const int nchunks = chunk > 0 ? (next + chunk - 1) / chunk : 1;
+    dim3 grid(blocks, nchunks);
+    k_sos_pass<1><<<grid, 32, 0, stream>>>(sp, x, tmp, y, nx, chunk, warm);
     D4W_CHECK_LAUNCH("k_sos_pass<fwd>");
-    k_sos_pass<-1><<<blocks, 32, 0, stream>>>(sp, x, tmp, y, nx);
+    k_sos_pass<-1><<<grid, 32, 0, stream>>>(sp, x, tmp, y, nx, chunk, warm);
     D4W_CHECK_LAUNCH("k_sos_pass<bwd>");
     return D4W_OK;
 }

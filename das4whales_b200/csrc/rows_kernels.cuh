@@ -249,46 +249,52 @@ __device__ __forceinline__ float ext_value(const float* __restrict__ r, int e, i
     return r[i];
 }
 
-// One warp = 32 channels; time is walked in tiles of 32 samples staged through shared memory so
-// global accesses stay coalesced while each lane runs its channel's recursion in double.
+// One warp = 32 channels x one time chunk; time is walked in tiles of 32 samples staged through shared
+// memory so global accesses stay coalesced while each lane runs its channel's recursion in double.
 // DIR = +1: forward pass over the extended signal, writes tmp[nx][next];
 // DIR = -1: backward pass over tmp, writes the central ns samples to y.
+// Time chunking (chunk > 0): blockIdx.y owns extended samples [c*chunk, (c+1)*chunk) of the pass's own
+// direction of travel and starts `warm` samples earlier from a zero state; the poles' decay (host picks
+// warm so that |p|max^warm < 1e-9) makes the result identical to the sequential recursion at fp32
+// precision.  Chunk 0 starts from SciPy's steady-state initial condition zi * first sample.
 template <int DIR>
 static __global__ void __launch_bounds__(32)
-k_sos_pass(SosParams sp, const float* __restrict__ x, float* __restrict__ tmp, float* __restrict__ y, int nx) {
+k_sos_pass(SosParams sp, const float* __restrict__ x, float* __restrict__ tmp, float* __restrict__ y, int nx, int chunk,
+           int warm) {
     __shared__ float tile[32][33];
     const int lane = threadIdx.x;
     const int ch0 = blockIdx.x * 32;
     const int ns = sp.ns, pad = sp.pad, next = ns + 2 * pad;
     const int ch = ch0 + lane;
     const bool live = ch < nx;
+    // progress index p = 0..next-1 along the direction of travel; extended index e = p (fwd) or next-1-p (bwd)
+    const int p_lo = (chunk > 0) ? (int)blockIdx.y * chunk : 0;            // first sample this block must OUTPUT
+    const int p_hi = (chunk > 0) ? min(next, p_lo + chunk) : next;
+    const int p_start = (chunk > 0 && blockIdx.y > 0) ? max(0, p_lo - warm) : 0;
+    if (p_lo >= next) return;
     double z0[kMaxSections], z1[kMaxSections];
-    // initial state: zi * first sample of the sequence being filtered (scipy sosfiltfilt)
     float first = 0.f;
-    if (live) {
+    if (live && p_start == 0) {
         if (DIR > 0) first = ext_value(x + (size_t)ch * ns, 0, pad, ns);
         else first = tmp[(size_t)ch * next + (next - 1)];
     }
 #pragma unroll
     for (int s = 0; s < kMaxSections; ++s) { z0[s] = sp.zi0[s] * (double)first; z1[s] = sp.zi1[s] * (double)first; }
-    const int ntiles = (next + 31) / 32;
-    for (int tix = 0; tix < ntiles; ++tix) {
-        const int e0 = (DIR > 0) ? tix * 32 : next - 32 * (tix + 1);     // tile covers e0 .. e0+31 (may start < 0)
-        // stage in: lane = time, loop over channels
+    for (int p0 = p_start; p0 < p_hi; p0 += 32) {
+        // stage in: lane = progress offset, loop over channels
         for (int c = 0; c < 32; ++c) {
             const int cc = ch0 + c;
-            const int e = e0 + lane;
+            const int p = p0 + lane;
+            const int e = (DIR > 0) ? p : next - 1 - p;
             float v = 0.f;
-            if (cc < nx && e >= 0 && e < next) v = (DIR > 0) ? ext_value(x + (size_t)cc * ns, e, pad, ns) : tmp[(size_t)cc * next + e];
+            if (cc < nx && p < p_hi) v = (DIR > 0) ? ext_value(x + (size_t)cc * ns, e, pad, ns) : tmp[(size_t)cc * next + e];
             tile[c][lane] = v;
         }
         __syncwarp();
         if (live) {
-            for (int q = 0; q < 32; ++q) {
-                const int k = (DIR > 0) ? q : 31 - q;
-                const int e = e0 + k;
-                if (e < 0 || e >= next) continue;
-                double v = (double)tile[lane][k];
+            const int qn = min(32, p_hi - p0);
+            for (int q = 0; q < qn; ++q) {
+                double v = (double)tile[lane][q];
 #pragma unroll
                 for (int s = 0; s < kMaxSections; ++s) {
                     if (s < sp.nsec) {
@@ -298,14 +304,15 @@ k_sos_pass(SosParams sp, const float* __restrict__ x, float* __restrict__ tmp, f
                         v = o;
                     }
                 }
-                tile[lane][k] = (float)v;
+                tile[lane][q] = (float)v;
             }
         }
         __syncwarp();
         for (int c = 0; c < 32; ++c) {
             const int cc = ch0 + c;
-            const int e = e0 + lane;
-            if (cc < nx && e >= 0 && e < next) {
+            const int p = p0 + lane;
+            if (cc < nx && p >= p_lo && p < p_hi) {
+                const int e = (DIR > 0) ? p : next - 1 - p;
                 if (DIR > 0) tmp[(size_t)cc * next + e] = tile[c][lane];
                 else { const int i = e - pad; if (i >= 0 && i < ns) y[(size_t)cc * ns + i] = tile[c][lane]; }
             }
