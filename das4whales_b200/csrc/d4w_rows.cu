@@ -28,7 +28,7 @@ extern "C" int d4w_fft_plan_create(d4w_fft_plan** out, int n, int device) {
     auto p = new d4w_fft_plan();
     p->n = n; p->device = device; p->smem_cap = prop.sharedMemPerBlockOptin;
     std::string err;
-    if (!make_plan(n, env_int("D4W_BLOCK_MAX_RADIX", 25), p->pl, err)) { delete p; return fail(D4W_ERR_UNSUPPORTED, err); }
+    if (!make_plan(n, env_int("D4W_BLOCK_MAX_RADIX", 25), p->pl, err, 128, 16)) { delete p; return fail(D4W_ERR_UNSUPPORTED, err); }
     p->pos2k = make_pos2freq(p->pl);
     std::vector<int> k2pos((size_t)n);
     for (int i = 0; i < n; ++i) k2pos[p->pos2k[i]] = i;

@@ -15,35 +15,86 @@ inline const std::vector<int>& inreg_radices() {
     return r;
 }
 
-// minimum-stage split of a 2^a 3^b 5^c number into in-register radices <= max_radix
-inline bool split_smooth(int m, int max_radix, std::vector<int>& out) {
-    std::map<int, std::vector<int>> memo;
-    struct Rec {
-        std::map<int, std::vector<int>>& memo; int maxr;
-        bool go(int m, std::vector<int>& res) {
-            if (m == 1) { res.clear(); return true; }
-            auto it = memo.find(m);
-            if (it != memo.end()) { res = it->second; return !res.empty(); }
-            std::vector<int> best;
-            for (int r : inreg_radices()) {
-                if (r > maxr || m % r) continue;
-                std::vector<int> sub;
-                if (!go(m / r, sub)) continue;
-                sub.insert(sub.begin(), r);
-                if (best.empty() || sub.size() < best.size()) best = sub;
+// Stage order used everywhere: generic primes first, then even radices (descending), then odd ones, so the
+// late short-stride stages have odd strides.
+inline std::vector<int> order_radices(const std::vector<int>& generic, const std::vector<int>& smooth) {
+    std::vector<int> ev, od;
+    for (int r : smooth) (r % 2 == 0 ? ev : od).push_back(r);
+    std::sort(ev.rbegin(), ev.rend());
+    std::sort(od.rbegin(), od.rend());
+    std::vector<int> order = generic;
+    order.insert(order.end(), ev.begin(), ev.end());
+    order.insert(order.end(), od.begin(), od.end());
+    return order;
+}
+
+// Cost model of one plan (scripts/bank_conflict_sim.py in C++): sum over stages of
+//   butterfly rounds = ceil((n/r)/threads)  x  shared-memory wavefronts per ideal wavefront,
+// where `lanes` = 8 for the 16-byte dual elements (quarter-warp phases), 16 for 8-byte elements.
+inline double plan_cost(int n, const std::vector<int>& order, int threads, int lanes) {
+    double total = 0.0;
+    int ns = n;
+    for (int r : order) {
+        const int L = ns / r, per = n / r;
+        long wf = 0, cnt = 0;
+        const int step = std::max(1, per / 512) * lanes;          // sample the lane groups of long stages
+        for (int id0 = 0; id0 < per; id0 += step) {
+            int groups[16];
+            for (int q = 0; q < r; ++q) {
+                for (int g = 0; g < lanes; ++g) groups[g] = 0;
+                int mx = 0;
+                for (int i = id0; i < std::min(per, id0 + lanes); ++i) {
+                    const int b = i / L, nn = i - b * L;
+                    const int g = (int)(((long)b * ns + nn + (long)q * L) % lanes);
+                    mx = std::max(mx, ++groups[g]);
+                }
+                wf += mx; ++cnt;
             }
-            memo[m] = best;
-            res = best;
-            return !best.empty();
         }
-    } rec{memo, max_radix};
-    return rec.go(m, out);
+        const double conflict = cnt ? (double)wf / (double)cnt : 1.0;
+        const double rounds = (double)((per + threads - 1) / threads);
+        total += rounds * conflict;
+        ns = L;
+    }
+    return total;
+}
+
+// minimum-stage split of a 2^a 3^b 5^c number into in-register radices <= max_radix; among the splits
+// with the fewest stages pick the cheapest under plan_cost.
+inline bool split_smooth(int m, int max_radix, std::vector<int>& out, int n_total = 0, int threads = 256, int lanes = 16,
+                         const std::vector<int>& generic = std::vector<int>()) {
+    if (n_total <= 0) n_total = m;
+    std::vector<int> best, cur;
+    double best_cost = -1.0;
+    size_t best_size = 0;
+    struct Rec {
+        int maxr, n_total, threads, lanes; const std::vector<int>& generic;
+        std::vector<int>& best; double& best_cost; size_t& best_size; std::vector<int>& cur;
+        void go(int m, int last) {
+            if (m == 1) {
+                if (!best.empty() && cur.size() > best_size) return;
+                const double c = plan_cost(n_total, order_radices(generic, cur), threads, lanes);
+                if (best.empty() || cur.size() < best_size || c < best_cost) { best = cur; best_cost = c; best_size = cur.size(); }
+                return;
+            }
+            if (!best.empty() && cur.size() >= best_size) return;
+            for (int r : inreg_radices()) {
+                if (r > maxr || r > last || m % r) continue;
+                cur.push_back(r);
+                go(m / r, r);
+                cur.pop_back();
+            }
+        }
+    } rec{max_radix, n_total, threads, lanes, generic, best, best_cost, best_size, cur};
+    rec.go(m, 1 << 30);
+    out = best;
+    return m == 1 || !best.empty();
 }
 
 // Build the stage schedule for length n.  Primes 7..61 become generic stages (first, where
 // the leg spacing is long and contiguous); then even radices (descending), then odd ones, so
 // the late short-stride stages are odd strides (bank-conflict free for 8-byte words).
-inline bool make_plan(int n, int max_radix, FftPlan& pl, std::string& err) {
+inline bool make_plan(int n, int max_radix, FftPlan& pl, std::string& err, int threads = 256, int lanes = 16) {
     if (n < 1) { err = "FFT length must be >= 1"; return false; }
     std::vector<int> generic;
     int m = n;
@@ -62,14 +113,8 @@ inline bool make_plan(int n, int max_radix, FftPlan& pl, std::string& err) {
         return false;
     }
     std::vector<int> smooth;
-    if (m > 1 && !split_smooth(m, max_radix, smooth)) { err = "cannot factor " + std::to_string(n); return false; }
-    std::vector<int> ev, od;
-    for (int r : smooth) (r % 2 == 0 ? ev : od).push_back(r);
-    std::sort(ev.rbegin(), ev.rend());
-    std::sort(od.rbegin(), od.rend());
-    std::vector<int> order = generic;
-    order.insert(order.end(), ev.begin(), ev.end());
-    order.insert(order.end(), od.begin(), od.end());
+    if (m > 1 && !split_smooth(m, max_radix, smooth, n, threads, lanes, generic)) { err = "cannot factor " + std::to_string(n); return false; }
+    std::vector<int> order = order_radices(generic, smooth);
     if ((int)order.size() > kMaxStages) { err = "too many FFT stages"; return false; }
     pl.n = n;
     pl.nstages = (int)order.size();

@@ -78,7 +78,7 @@ inline int build_fk_hostplan(int nx, int ns, size_t smem_cap, FkHostPlan& hp, st
     if (hp.tma) { hp.fstride = (nx + 255) / 256 * 256; hp.col_smem = (size_t)hp.fstride * 16; }
     const char* col_spec = std::getenv("D4W_COL_PLAN");
     if (!(col_spec && *col_spec && make_plan_from_string(nx, col_spec, hp.colpl)) &&
-        !make_plan(nx, hp.dual ? std::min(col_maxr, env_int("D4W_DUAL_MAX_RADIX", 25)) : col_maxr, hp.colpl, e2)) { err = "channel axis: " + e2; return 1; }
+        !make_plan(nx, hp.dual ? std::min(col_maxr, env_int("D4W_DUAL_MAX_RADIX", 25)) : col_maxr, hp.colpl, e2, 256, hp.dual ? 8 : 16)) { err = "channel axis: " + e2; return 1; }
 
     // time axis = T1 (registers) x T2 (shared memory).  Dual-lane row kernel (default): T2 <= 6144 keeps the
     // 16-byte-element tile under 96 KB -> two CTAs per SM; scalar kernel: T2 <= 10240 (16384 when T1 == 1).
@@ -94,7 +94,7 @@ inline int build_fk_hostplan(int nx, int ns, size_t smem_cap, FkHostPlan& hp, st
         if (forced_t1 == 0 && t2 > limit) continue;
         if ((size_t)t2 * (hp.row_dual ? 16 : 8) > smem_cap - 1024) continue;
         FftPlan tmp;
-        if (!make_plan(t2, row_maxr_eff, tmp, e2)) continue;
+        if (!make_plan(t2, row_maxr_eff, tmp, e2, hp.row_dual ? 128 : 256, hp.row_dual ? 8 : 16)) continue;
         t1 = cand; hp.rowpl = tmp;
         break;
     }
