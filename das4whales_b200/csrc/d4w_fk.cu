@@ -72,6 +72,12 @@ struct d4w_fk_plan {
     int *d_k2pos = nullptr, *d_pos2k = nullptr, *d_pos2k_row = nullptr;
     float* d_taper = nullptr;
     unsigned long long* d_dbg = nullptr;      // 8 phase-cycle counters (D4W_FK_DEBUG=1)
+    // two-level column transform
+    int two_level = 0;
+    Col2Params col2{};
+    float2* d_tw_x2 = nullptr;
+    size_t colb_smem = 0;
+    FkHostPlan hostplan;                      // kept for mask-time table building
     std::vector<int> h_k2pos;
     int col_threads = 256, row_threads = 256;
     size_t col_smem = 0, row_smem = 0;
@@ -86,6 +92,8 @@ struct d4w_fk_mask {
     std::vector<int> act_k;
     int *d_act_k = nullptr, *d_k2slot = nullptr;
     int2* d_slot_pos = nullptr;
+    int* d_plane_ptr = nullptr;
+    Col2Entry* d_ents = nullptr;
     float* d_table = nullptr;      // caller-owned
 };
 
@@ -122,6 +130,7 @@ extern "C" int d4w_fk_plan_create(d4w_fk_plan** out, int nx, int ns, int device)
     const auto &p2k = hp.pos2k, &k2p = hp.k2pos, &p2kr = hp.pos2k_row;
     const auto& tap = hp.taper;
     pl->h_k2pos = hp.k2pos;
+    pl->hostplan = hp;
     cudaError_t e = cudaSuccess;
     if (e == cudaSuccess) e = upload(&pl->d_tw_col, twc);
     if (e == cudaSuccess) e = upload(&pl->d_tw_row, twr);
@@ -130,6 +139,7 @@ extern "C" int d4w_fk_plan_create(d4w_fk_plan** out, int nx, int ns, int device)
     if (e == cudaSuccess) e = upload(&pl->d_k2pos, k2p);
     if (e == cudaSuccess) e = upload(&pl->d_pos2k_row, p2kr);
     if (e == cudaSuccess) e = upload(&pl->d_taper, tap);
+    if (e == cudaSuccess && hp.two_level) e = upload(&pl->d_tw_x2, hp.tw_x2);
     if (e == cudaSuccess && env_int("D4W_FK_DEBUG", 0)) { e = cudaMalloc((void**)&pl->d_dbg, 64); if (e == cudaSuccess) e = cudaMemset(pl->d_dbg, 0, 64); }
     // the attribute is per-kernel global state: always raise it to the device maximum, never to a plan's own size
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_col_fwd<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
@@ -157,6 +167,14 @@ extern "C" int d4w_fk_plan_create(d4w_fk_plan** out, int nx, int ns, int device)
     }
     pl->col.tw = pl->d_tw_col; pl->col.k2pos = pl->d_k2pos; pl->col.pos2k = pl->d_pos2k;
     pl->row.tw = pl->d_tw_row; pl->row.twT = pl->d_twT;
+    if (hp.two_level) {
+        pl->two_level = 1; pl->colb_smem = hp.colb_smem;
+        pl->col2.plb = hp.plb; pl->col2.twb = pl->d_tw_x2; pl->col2.twn = pl->d_tw_col;
+        pl->col2.nx = nx; pl->col2.ns = ns; pl->col2.x1 = hp.x1; pl->col2.x2 = hp.x2; pl->col2.planes = hp.planes;
+        pl->col2.np = hp.np2; pl->col2.fstride = hp.fstride2;
+        cudaFuncSetAttribute(k_colB_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
+        cudaFuncSetAttribute(k_colB_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
+    }
     *out = pl;
     return D4W_OK;
 }
@@ -165,7 +183,7 @@ extern "C" int d4w_fk_plan_destroy(d4w_fk_plan* pl) {
     if (!pl) return D4W_OK;
     DeviceGuard guard(pl->device);
     cudaFree(pl->d_tw_col); cudaFree(pl->d_tw_row); cudaFree(pl->d_twT);
-    cudaFree(pl->d_k2pos); cudaFree(pl->d_pos2k); cudaFree(pl->d_pos2k_row); cudaFree(pl->d_taper); cudaFree(pl->d_dbg);
+    cudaFree(pl->d_k2pos); cudaFree(pl->d_pos2k); cudaFree(pl->d_pos2k_row); cudaFree(pl->d_taper); cudaFree(pl->d_dbg); cudaFree(pl->d_tw_x2);
     delete pl;
     return D4W_OK;
 }
@@ -224,6 +242,15 @@ static int mask_finish_support(d4w_fk_mask* m, void* stream_v) {
         slot_pos[sl] = make_int2(pl->h_k2pos[k], pl->h_k2pos[k == 0 ? 0 : pl->nx - k]);
     }
     D4W_CUDA_TRY(upload(&m->d_slot_pos, slot_pos));
+    if (pl->two_level) {
+        std::vector<int> plane_ptr; std::vector<Col2EntryHost> ents;
+        build_col2_entries(pl->hostplan, k2slot, plane_ptr, ents);
+        static_assert(sizeof(Col2EntryHost) == sizeof(Col2Entry), "entry layout");
+        std::vector<Col2Entry> dev((size_t)ents.size());
+        for (size_t i = 0; i < ents.size(); ++i) dev[i] = Col2Entry{ents[i].pos, ents[i].slot, ents[i].flags, 0};
+        D4W_CUDA_TRY(upload(&m->d_plane_ptr, plane_ptr));
+        D4W_CUDA_TRY(upload(&m->d_ents, dev));
+    }
     return D4W_OK;
 }
 
@@ -275,7 +302,7 @@ extern "C" int d4w_fk_mask_create_dense(d4w_fk_mask** out, d4w_fk_plan* plan, co
 extern "C" int d4w_fk_mask_destroy(d4w_fk_mask* m) {
     if (!m) return D4W_OK;
     DeviceGuard guard(m->device);
-    cudaFree(m->d_h); cudaFree(m->d_act_k); cudaFree(m->d_k2slot); cudaFree(m->d_slot_pos);
+    cudaFree(m->d_h); cudaFree(m->d_act_k); cudaFree(m->d_k2slot); cudaFree(m->d_slot_pos); cudaFree(m->d_plane_ptr); cudaFree(m->d_ents);
     delete m;
     return D4W_OK;
 }
@@ -318,7 +345,10 @@ extern "C" int d4w_fk_mask_materialize(const d4w_fk_mask* m, double* dev_out, vo
 // ------------------------------------------------------------------------------- apply
 extern "C" size_t d4w_fk_workspace_bytes(const d4w_fk_plan* pl, const d4w_fk_mask* m) {
     if (!pl || !m) return 0;
-    return std::max<size_t>((size_t)m->nact * pl->ns * sizeof(float2), 16);
+    size_t b = std::max<size_t>((size_t)m->nact * pl->ns * sizeof(float2), 16);
+    b = (b + 255) / 256 * 256;
+    if (pl->two_level) b += (size_t)pl->col2.planes * pl->col2.x2 * pl->ns * sizeof(float2);     // level-A/B intermediate V
+    return b;
 }
 
 template <bool INV>
@@ -362,10 +392,30 @@ extern "C" int d4w_fk_apply_pass_ex(d4w_fk_plan* pl, d4w_fk_mask* m, const float
     const int tile = pl->col.dual ? 4 * pl->col.npair : 2 * pl->col.nc;
     const int ntiles = (pl->ns + tile - 1) / tile;
     const float* tap = taper ? mp->d_taper + t_offset : nullptr;
+    const bool two = pl->two_level && pl == mp && m->d_ents && ((uintptr_t)ws % 16 == 0);
+    cpd* v2 = nullptr;
+    if (two) {
+        size_t wb = std::max<size_t>((size_t)nact * pl->ns * sizeof(float2), 16);
+        wb = (wb + 255) / 256 * 256;
+        v2 = reinterpret_cast<cpd*>(reinterpret_cast<char*>(ws) + wb);
+    }
     switch (pass) {
         case 1:
             if (!x) return fail(D4W_ERR_ARG, "d4w_fk_apply: null input");
             if (nact == 0) return D4W_OK;
+            if (two && ((uintptr_t)x % 16 == 0)) {
+                dim3 ga((pl->ns / 4 + 127) / 128, pl->col2.x2);
+                switch (pl->col2.x1) {
+                    case 25: k_colA_fwd<25><<<ga, 128, 0, stream>>>(pl->col2, x, v2, tap); break;
+                    case 20: k_colA_fwd<20><<<ga, 128, 0, stream>>>(pl->col2, x, v2, tap); break;
+                    default: k_colA_fwd<16><<<ga, 128, 0, stream>>>(pl->col2, x, v2, tap); break;
+                }
+                D4W_CHECK_LAUNCH("k_colA_fwd");
+                dim3 gb((pl->ns / 2 + pl->col2.np - 1) / pl->col2.np, pl->col2.planes);
+                k_colB_fwd<<<gb, 128, pl->colb_smem, stream>>>(pl->col2, v2, w, ldw, m->d_plane_ptr, m->d_ents);
+                D4W_CHECK_LAUNCH("k_colB_fwd");
+                return D4W_OK;
+            }
             if (pl->col.tma && ((uintptr_t)x % 16 == 0)) {
                 CUtensorMap tm;
                 if (make_tile_map(&tm, x, pl->nx, pl->ns)) {
@@ -420,6 +470,19 @@ extern "C" int d4w_fk_apply_pass_ex(d4w_fk_plan* pl, d4w_fk_mask* m, const float
             return launch_row_split<true>(pl, w, slot_count, stream);
         case 5:
             if (!y) return fail(D4W_ERR_ARG, "d4w_fk_apply: null output");
+            if (two && ((uintptr_t)y % 16 == 0)) {
+                dim3 gb((pl->ns / 2 + pl->col2.np - 1) / pl->col2.np, pl->col2.planes);
+                k_colB_inv<<<gb, 128, pl->colb_smem, stream>>>(pl->col2, v2, w, ldw, m->d_plane_ptr, m->d_ents);
+                D4W_CHECK_LAUNCH("k_colB_inv");
+                dim3 ga((pl->ns / 4 + 127) / 128, pl->col2.x2);
+                switch (pl->col2.x1) {
+                    case 25: k_colA_inv<25><<<ga, 128, 0, stream>>>(pl->col2, v2, y); break;
+                    case 20: k_colA_inv<20><<<ga, 128, 0, stream>>>(pl->col2, v2, y); break;
+                    default: k_colA_inv<16><<<ga, 128, 0, stream>>>(pl->col2, v2, y); break;
+                }
+                D4W_CHECK_LAUNCH("k_colA_inv");
+                return D4W_OK;
+            }
             if (pl->col.tma && ((uintptr_t)y % 16 == 0)) {
                 CUtensorMap tm;
                 if (make_tile_map(&tm, y, pl->nx, pl->ns)) {

@@ -12,6 +12,12 @@ struct FkHostPlan {
     int t1 = 1, t2 = 0, nc = 1, nc_shift = 0, fstride = 0, aligned = 0;
     int dual = 0, npair = 0, npair_shift = 0, aligned16 = 0, tma = 0, col_max_radix = 0;
     int row_dual = 0;
+    // two-level column transform (nx = x1 * x2), see fk_kernels.cuh
+    int two_level = 0, x1 = 0, x2 = 0, planes = 0, np2 = 0, fstride2 = 0;
+    FftPlan plb{};
+    std::vector<float2> tw_x2;
+    std::vector<int> pos_x2;        // k2 -> position after the level-B forward transform
+    size_t colb_smem = 0;
     FftPlan colpl{}, rowpl{};
     std::vector<float2> tw_col, tw_row, twT;
     std::vector<int> pos2k, k2pos, pos2k_row;
@@ -118,6 +124,28 @@ inline int build_fk_hostplan(int nx, int ns, size_t smem_cap, FkHostPlan& hp, st
               " has no supported split (needs ns = T1*T2 with T1 <= 25, T2 <= 6144 (10240 scalar) and prime factors <= 61)";
         return 1;
     }
+    // ---- two-level column split: X1 in registers (largest of 25, 20, 16), X2-point smem FFT
+    if (env_int("D4W_COL_TWO_LEVEL", 1) && ns % 4 == 0) {
+        const int forced_x1 = env_int("D4W_COL_X1", 0);
+        for (int cand : {25, 20, 16}) {
+            if (forced_x1 && cand != forced_x1) continue;
+            if (nx % cand) continue;
+            const int x2 = nx / cand;
+            if (x2 < 8 || x2 > 1024) continue;
+            FftPlan tmp;
+            if (!make_plan(x2, 25, tmp, e2, 128, 8)) continue;
+            int np = 8;
+            while (np > 1 && (size_t)np * (x2 | 1) * 16 > 56 * 1024) np >>= 1;
+            if ((size_t)np * (x2 | 1) * 16 > 100 * 1024) continue;
+            hp.two_level = 1; hp.x1 = cand; hp.x2 = x2; hp.planes = cand / 2 + 1; hp.np2 = np; hp.fstride2 = x2 | 1;
+            hp.plb = tmp; hp.colb_smem = (size_t)np * hp.fstride2 * 16;
+            hp.tw_x2 = make_twiddles(x2);
+            auto p2k = make_pos2freq(tmp);
+            hp.pos_x2.assign((size_t)x2, 0);
+            for (int p = 0; p < x2; ++p) hp.pos_x2[p2k[p]] = p;
+            break;
+        }
+    }
     for (int st = 0; st < hp.colpl.nstages; ++st) hp.col_max_radix = std::max(hp.col_max_radix, hp.colpl.radix[st]);
     hp.t1 = t1; hp.t2 = ns / t1;
     hp.row_smem = (size_t)hp.t2 * (hp.row_dual ? 16 : sizeof(float2));
@@ -134,6 +162,41 @@ inline int build_fk_hostplan(int nx, int ns, size_t smem_cap, FkHostPlan& hp, st
     hp.pos2k_row = make_pos2freq(hp.rowpl);
     hp.taper = tukey_window(ns, 0.03);
     return 0;
+}
+
+
+// per-plane output/input table of the two-level column transform: for plane k1' the level-B transform
+// P[k2] equals X[k1' + X1*k2]; by Hermitian symmetry X[(X1-k1') + X1*k2] = conj(P[X2-1-k2]).
+struct Col2EntryHost { int pos, slot, flags, pad; };
+inline void build_col2_entries(const FkHostPlan& hp, const std::vector<int>& k2slot /* size nx/2+1, -1 = pruned */,
+                               std::vector<int>& plane_ptr, std::vector<Col2EntryHost>& ents) {
+    const int nx = hp.nx, x1 = hp.x1, x2 = hp.x2;
+    plane_ptr.assign((size_t)hp.planes + 1, 0);
+    ents.clear();
+    auto slot_of = [&](int k) { return (k >= 0 && 2 * k <= nx) ? k2slot[k] : -1; };
+    for (int pl = 0; pl < hp.planes; ++pl) {
+        plane_ptr[pl] = (int)ents.size();
+        const bool self = (pl == 0) || (2 * pl == x1);
+        for (int k2 = 0; k2 < x2; ++k2) {
+            const int k = pl + x1 * k2;
+            if (2 * k <= nx) {                               // direct: P[k2] = X[k]
+                const int sl = slot_of(k);
+                if (sl >= 0) ents.push_back({hp.pos_x2[k2], sl, 2, 0});
+            } else {                                         // upper half: P[k2] = conj(X[nx - k]) (inverse only)
+                const int sl = slot_of(nx - k);
+                if (sl >= 0 && self) ents.push_back({hp.pos_x2[k2], sl, 1, 0});
+            }
+        }
+        if (!self) {
+            for (int k2 = 0; k2 < x2; ++k2) {                // mirror plane: X[(x1-pl) + x1*k2] = conj(P[x2-1-k2])
+                const int kk = (x1 - pl) + x1 * k2;
+                const int sl = slot_of(kk);
+                if (sl >= 0) ents.push_back({hp.pos_x2[x2 - 1 - k2], sl, 3, 0});
+            }
+            // entries of this plane above nx/2 whose mirror lies in the partner plane are exactly the ones above
+        }
+    }
+    plane_ptr[hp.planes] = (int)ents.size();
 }
 
 }  // namespace d4w

@@ -468,6 +468,134 @@ __host__ __device__ inline void body_row_mid_dual(const RowParams& rp, float2* _
     }
 }
 
+
+// ================================================================== two-level column transform (nx = X1 * X2)
+// Channel c = X2*c1 + c2, wavenumber k = k1 + X1*k2:
+//   level A: radix-X1 DFT over c1 (rows X2 apart) entirely in registers, times W_nx^{c2 k1}      (streaming)
+//   level B: X2-point FFT over c2 in shared memory, wide coalesced tiles, several CTAs per SM
+// Real input => only planes k1 = 0..X1/2 of the intermediate V are stored (Hermitian in k1), and the
+// outputs of plane X1-k1 are conj(P_{k1}[X2-1-k2]) of the same level-B transform, so each kept
+// wavenumber row is produced exactly once.  V[plane][c2][sample pair] holds 16-byte elements
+// {re_t, re_t+1, im_t, im_t+1}.  Forward: A then B (pruned rows out); inverse: B then A.
+struct Col2Params {
+    FftPlan plb;             // X2-point plan (dual lanes)
+    const float2* twb;       // W_X2^j
+    const float2* twn;       // W_nx^j
+    int nx, ns, x1, x2, planes, np, fstride;
+};
+struct Col2Entry { int pos, slot, flags, pad; };     // flags bit0: conjugate, bit1: stored by the forward pass
+
+template <int X1>
+__host__ __device__ inline void body_colA_fwd(const Col2Params& cp, const float* __restrict__ x, cpd* __restrict__ v2,
+                                              const float* __restrict__ taper, int c2, int t4) {
+    const int ns = cp.ns, x2 = cp.x2;
+    const size_t hp = (size_t)(ns / 2);
+    cpd v[X1];
+    f2x ta = vbc(1.f), tb = vbc(1.f);
+    if (taper) { ta = f2x_set(taper[4 * t4], taper[4 * t4 + 1]); tb = f2x_set(taper[4 * t4 + 2], taper[4 * t4 + 3]); }
+    static_for<X1>([&](auto c1c) {
+        constexpr int c1 = decltype(c1c)::value;
+        const float4 a = *reinterpret_cast<const float4*>(x + (size_t)(x2 * c1 + c2) * ns + 4 * t4);
+        v[c1] = dmake(f2x_set(a.x, a.y), f2x_set(a.z, a.w));
+        if (taper) { v[c1].x = vmul(v[c1].x, ta); v[c1].y = vmul(v[c1].y, tb); }
+    });
+    DFTD<X1, false>::run(v);
+    const f2x half = vbc(0.5f);
+    static_for<X1 / 2 + 1>([&](auto kc) {
+        constexpr int k1 = decltype(kc)::value;
+        const cpd z = v[outpos<X1>(k1)], z2 = v[outpos<X1>((X1 - k1) % X1)];
+        cpd fa = dmake(vmul(vadd(z.x, z2.x), half), vmul(vsub(z.y, z2.y), half));     // lanes F_t, F_t+1
+        cpd fb = dmake(vmul(vadd(z.y, z2.y), half), vmul(vsub(z2.x, z.x), half));     // lanes F_t+2, F_t+3
+        if (k1 > 0) { const float2 w = cp.twn[c2 * k1]; fa = dmul_s(fa, w); fb = dmul_s(fb, w); }
+        cpd* o = v2 + ((size_t)k1 * x2 + c2) * hp + 2 * t4;
+        o[0] = fa; o[1] = fb;
+    });
+}
+
+template <int X1>
+__host__ __device__ inline void body_colA_inv(const Col2Params& cp, const cpd* __restrict__ v2, float* __restrict__ y, int c2, int t4) {
+    const int ns = cp.ns, x2 = cp.x2;
+    const size_t hp = (size_t)(ns / 2);
+    cpd v[X1];
+    static_for<X1 / 2 + 1>([&](auto kc) {
+        constexpr int k1 = decltype(kc)::value;
+        const cpd* in = v2 + ((size_t)k1 * x2 + c2) * hp + 2 * t4;
+        cpd fa = in[0], fb = in[1];
+        if (k1 > 0) { const float2 w = cp.twn[c2 * k1]; fa = dmulc_s(fa, w); fb = dmulc_s(fb, w); }
+        if (k1 == 0 || 2 * k1 == X1) {                       // self-conjugate in k1: real
+            v[k1] = dmake(fa.x, fb.x);
+        } else {
+            v[k1] = dmake(vsub(fa.x, fb.y), vadd(fa.y, fb.x));            // F_a + i F_b
+            v[X1 - k1] = dmake(vadd(fa.x, fb.y), vsub(fb.x, fa.y));       // conj(F_a) + i conj(F_b)
+        }
+    });
+    DFTD<X1, true>::run(v);
+    static_for<X1>([&](auto c1c) {
+        constexpr int c1 = decltype(c1c)::value;
+        const cpd z = v[outpos<X1>(c1)];
+        *reinterpret_cast<float4*>(y + (size_t)(x2 * c1 + c2) * ns + 4 * t4) = make_float4(f2x_lo(z.x), f2x_hi(z.x), f2x_lo(z.y), f2x_hi(z.y));
+    });
+}
+
+// level B forward: one plane, np consecutive sample pairs; writes the kept wavenumber rows
+__host__ __device__ inline void body_colB_fwd(const Col2Params& cp, const cpd* __restrict__ v2, float2* __restrict__ w, size_t ldw,
+                                              const int* __restrict__ plane_ptr, const Col2Entry* __restrict__ ents, int plane,
+                                              int tile, int tid, int nthr, cpd* smem) {
+    const int x2 = cp.x2, np = cp.np, hp = cp.ns / 2;
+    const int tp0 = tile * np;
+    const cpd zero = dmake(vbc(0.f), vbc(0.f));
+    for (int i = tid; i < x2 * np; i += nthr) {
+        const int c2 = i / np, j = i - c2 * np;
+        const cpd* src = v2 + ((size_t)plane * x2 + c2) * hp + tp0 + j;
+#ifdef __CUDA_ARCH__
+        if (tp0 + j < hp) cp_async16(smem + j * cp.fstride + c2, src); else smem[j * cp.fstride + c2] = zero;
+#else
+        smem[j * cp.fstride + c2] = (tp0 + j < hp) ? *src : zero;
+#endif
+    }
+#ifdef __CUDA_ARCH__
+    cp_async_wait_all();
+#endif
+    D4W_SYNC();
+    fft_forward_stages_dual(smem, cp.plb, cp.twb, np, cp.fstride, tid, nthr);
+    const int e0 = plane_ptr[plane], ne = plane_ptr[plane + 1] - e0;
+    for (int i = tid; i < ne * np; i += nthr) {
+        const int ei = i / np, j = i - ei * np;
+        const Col2Entry e = ents[e0 + ei];
+        if (!(e.flags & 2) || tp0 + j >= hp) continue;
+        cpd v = smem[j * cp.fstride + e.pos];
+        if (e.flags & 1) v.y = vneg(v.y);
+        *reinterpret_cast<float4*>(w + (size_t)e.slot * ldw + 2 * (tp0 + j)) = make_float4(f2x_lo(v.x), f2x_lo(v.y), f2x_hi(v.x), f2x_hi(v.y));
+    }
+}
+
+// level B inverse: kept rows -> plane of V
+__host__ __device__ inline void body_colB_inv(const Col2Params& cp, cpd* __restrict__ v2, const float2* __restrict__ w, size_t ldw,
+                                              const int* __restrict__ plane_ptr, const Col2Entry* __restrict__ ents, int plane,
+                                              int tile, int tid, int nthr, cpd* smem) {
+    const int x2 = cp.x2, np = cp.np, hp = cp.ns / 2;
+    const int tp0 = tile * np;
+    const cpd zero = dmake(vbc(0.f), vbc(0.f));
+    for (int i = tid; i < np * cp.fstride; i += nthr) smem[i] = zero;
+    D4W_SYNC();
+    const int e0 = plane_ptr[plane], ne = plane_ptr[plane + 1] - e0;
+    for (int i = tid; i < ne * np; i += nthr) {
+        const int ei = i / np, j = i - ei * np;
+        if (tp0 + j >= hp) continue;
+        const Col2Entry e = ents[e0 + ei];
+        const float4 u = *reinterpret_cast<const float4*>(w + (size_t)e.slot * ldw + 2 * (tp0 + j));
+        cpd v = dmake(f2x_set(u.x, u.z), f2x_set(u.y, u.w));
+        if (e.flags & 1) v.y = vneg(v.y);
+        smem[j * cp.fstride + e.pos] = v;
+    }
+    D4W_SYNC();
+    fft_inverse_stages_dual(smem, cp.plb, cp.twb, np, cp.fstride, tid, nthr);
+    for (int i = tid; i < x2 * np; i += nthr) {
+        const int c2 = i / np, j = i - c2 * np;
+        if (tp0 + j < hp) v2[((size_t)plane * x2 + c2) * hp + tp0 + j] = smem[j * cp.fstride + c2];
+    }
+}
+
 // ================================================================== __global__ wrappers
 #ifdef __CUDACC__
 extern __shared__ __align__(1024) float2 d4w_dyn_smem[];
@@ -742,6 +870,29 @@ static __global__ void __launch_bounds__(128, 2)     // radix-25 dual butterflie
 k_row_mid_dual(RowParams rp, float2* __restrict__ w, size_t ldw, const float* __restrict__ tab, size_t tab_slot_stride, int nslots) {
     body_row_mid_dual(rp, w, ldw, tab, tab_slot_stride, blockIdx.x, blockIdx.y, nslots, threadIdx.x, blockDim.x,
                       reinterpret_cast<cpd*>(d4w_dyn_smem));
+}
+
+template <int X1>
+static __global__ void __launch_bounds__(128)
+k_colA_fwd(Col2Params cp, const float* __restrict__ x, cpd* __restrict__ v2, const float* __restrict__ taper) {
+    const int t4 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t4 < cp.ns / 4) body_colA_fwd<X1>(cp, x, v2, taper, blockIdx.y, t4);
+}
+template <int X1>
+static __global__ void __launch_bounds__(128)
+k_colA_inv(Col2Params cp, const cpd* __restrict__ v2, float* __restrict__ y) {
+    const int t4 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t4 < cp.ns / 4) body_colA_inv<X1>(cp, v2, y, blockIdx.y, t4);
+}
+static __global__ void __launch_bounds__(128, 4)
+k_colB_fwd(Col2Params cp, const cpd* __restrict__ v2, float2* __restrict__ w, size_t ldw, const int* __restrict__ plane_ptr,
+           const Col2Entry* __restrict__ ents) {
+    body_colB_fwd(cp, v2, w, ldw, plane_ptr, ents, blockIdx.y, blockIdx.x, threadIdx.x, blockDim.x, reinterpret_cast<cpd*>(d4w_dyn_smem));
+}
+static __global__ void __launch_bounds__(128, 4)
+k_colB_inv(Col2Params cp, cpd* __restrict__ v2, const float2* __restrict__ w, size_t ldw, const int* __restrict__ plane_ptr,
+           const Col2Entry* __restrict__ ents) {
+    body_colB_inv(cp, v2, w, ldw, plane_ptr, ents, blockIdx.y, blockIdx.x, threadIdx.x, blockDim.x, reinterpret_cast<cpd*>(d4w_dyn_smem));
 }
 
 static __global__ void k_mask_rowmax(MaskParams mp, unsigned int* rowmax, int fchunk) {

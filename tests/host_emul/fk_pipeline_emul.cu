@@ -19,6 +19,20 @@ template <int T1> static void split_all(bool inv, float2* w, size_t ldw, int t2,
             else body_row_split<T1, false>(w, ldw, t2, twT, s, t);
         }
 }
+template <int X1> static void colA_all(bool inv, const Col2Params& c2p, const float* x, cpd* v2, float* y, const float* taper) {
+    for (int c2 = 0; c2 < c2p.x2; ++c2)
+        for (int t4 = 0; t4 < c2p.ns / 4; ++t4) {
+            if (inv) body_colA_inv<X1>(c2p, v2, y, c2, t4);
+            else body_colA_fwd<X1>(c2p, x, v2, taper, c2, t4);
+        }
+}
+static void colA_dispatch(bool inv, const Col2Params& c2p, const float* x, cpd* v2, float* y, const float* taper) {
+    switch (c2p.x1) {
+        case 25: colA_all<25>(inv, c2p, x, v2, y, taper); break;
+        case 20: colA_all<20>(inv, c2p, x, v2, y, taper); break;
+        default: colA_all<16>(inv, c2p, x, v2, y, taper); break;
+    }
+}
 static void split_dispatch(int t1, bool inv, float2* w, size_t ldw, int t2, const float2* twT, int nact) {
     switch (t1) {
 #define C(T) case T: split_all<T>(inv, w, ldw, t2, twT, nact); break;
@@ -68,7 +82,22 @@ int main(int argc, char** argv) {
     std::vector<float> y((size_t)nx * ns, -777.f);
     const size_t ldw = ns;
     const int tile = 2 * hp.nc, ntiles = (ns + tile - 1) / tile;
-    if (nact)
+    const bool two = hp.two_level && nact > 0;
+    Col2Params c2p{}; std::vector<cpd> v2; std::vector<int> plane_ptr; std::vector<Col2Entry> ents2;
+    if (two) {
+        c2p.plb = hp.plb; c2p.twb = hp.tw_x2.data(); c2p.twn = hp.tw_col.data(); c2p.nx = nx; c2p.ns = ns; c2p.x1 = hp.x1; c2p.x2 = hp.x2;
+        c2p.planes = hp.planes; c2p.np = hp.np2; c2p.fstride = hp.fstride2;
+        v2.resize((size_t)hp.planes * hp.x2 * (ns / 2));
+        std::vector<Col2EntryHost> eh; build_col2_entries(hp, k2slot, plane_ptr, eh);
+        for (auto& e : eh) ents2.push_back(Col2Entry{e.pos, e.slot, e.flags, 0});
+        smem.resize(std::max(smem.size(), hp.colb_smem / sizeof(float2) + 16));
+        colA_dispatch(false, c2p, x.data(), v2.data(), nullptr, taper ? hp.taper.data() : nullptr);
+        const int ntb = (ns / 2 + hp.np2 - 1) / hp.np2;
+        for (int pl = 0; pl < hp.planes; ++pl)
+            for (int tb = 0; tb < ntb; ++tb)
+                body_colB_fwd(c2p, v2.data(), w.data(), ldw, plane_ptr.data(), ents2.data(), pl, tb, 0, 1, reinterpret_cast<cpd*>(smem.data()));
+    }
+    if (nact && !two)
         for (int b = 0; b < ntiles; ++b) {
             if (hp.dual) body_col_fwd_dual(cp, x.data(), w.data(), ldw, slot_pos.data(), nact, taper ? hp.taper.data() : nullptr, b, 0, 1, reinterpret_cast<cpd*>(smem.data()));
             else body_col_fwd(cp, x.data(), w.data(), ldw, slot_pos.data(), nact, taper ? hp.taper.data() : nullptr, b, 0, 1, smem.data());
@@ -83,7 +112,14 @@ int main(int argc, char** argv) {
             for (int k1 = 0; k1 < hp.t1; ++k1) body_row_mid(rp, w.data(), ldw, tab.data(), (size_t)ns, k1, s, 0, 1, smem.data());
     }
     if (hp.t1 > 1 && nact) split_dispatch(hp.t1, true, w.data(), ldw, hp.t2, hp.twT.data(), nact);
-    for (int b = 0; b < ntiles; ++b) {
+    if (two) {
+        const int ntb = (ns / 2 + hp.np2 - 1) / hp.np2;
+        for (int pl = 0; pl < hp.planes; ++pl)
+            for (int tb = 0; tb < ntb; ++tb)
+                body_colB_inv(c2p, v2.data(), w.data(), ldw, plane_ptr.data(), ents2.data(), pl, tb, 0, 1, reinterpret_cast<cpd*>(smem.data()));
+        colA_dispatch(true, c2p, nullptr, v2.data(), y.data(), nullptr);
+    }
+    for (int b = 0; b < ntiles && !two; ++b) {
         if (hp.dual) body_col_inv_dual(cp, w.data(), ldw, slot_pos.data(), nact, y.data(), b, 0, 1, reinterpret_cast<cpd*>(smem.data()));
         else body_col_inv(cp, w.data(), ldw, slot_pos.data(), nact, y.data(), b, 0, 1, smem.data());
     }
@@ -91,7 +127,7 @@ int main(int argc, char** argv) {
     FILE* fo = fopen(argv[2], "wb");
     fwrite(y.data(), 4, y.size(), fo);
     fwrite(&nact, 4, 1, fo);
-    int info[4] = {hp.t1, hp.t2, hp.nc, hp.dual ? 100 + hp.colpl.nstages : hp.colpl.nstages};
+    int info[4] = {hp.t1, hp.t2, hp.nc, hp.two_level ? 1000 + hp.x1 : (hp.dual ? 100 + hp.colpl.nstages : hp.colpl.nstages)};
     fwrite(info, 4, 4, fo);
     fclose(fo);
     return 0;
