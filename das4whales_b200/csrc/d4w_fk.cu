@@ -77,6 +77,7 @@ struct d4w_fk_plan {
     Col2Params col2{};
     float2* d_tw_x2 = nullptr;
     size_t colb_smem = 0;
+    int colb_threads = 128;
     FkHostPlan hostplan;                      // kept for mask-time table building
     std::vector<int> h_k2pos;
     int col_threads = 256, row_threads = 256;
@@ -172,6 +173,8 @@ extern "C" int d4w_fk_plan_create(d4w_fk_plan** out, int nx, int ns, int device)
         pl->col2.plb = hp.plb; pl->col2.twb = pl->d_tw_x2; pl->col2.twn = pl->d_tw_col;
         pl->col2.nx = nx; pl->col2.ns = ns; pl->col2.x1 = hp.x1; pl->col2.x2 = hp.x2; pl->col2.planes = hp.planes;
         pl->col2.np = hp.np2; pl->col2.fstride = hp.fstride2;
+        pl->col2.np_shift = hp.np2 == 8 ? 3 : hp.np2 == 4 ? 2 : hp.np2 == 2 ? 1 : 0;
+        pl->colb_threads = hp.colb_threads;
         cudaFuncSetAttribute(k_colB_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
         cudaFuncSetAttribute(k_colB_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
     }
@@ -412,7 +415,7 @@ extern "C" int d4w_fk_apply_pass_ex(d4w_fk_plan* pl, d4w_fk_mask* m, const float
                 }
                 D4W_CHECK_LAUNCH("k_colA_fwd");
                 dim3 gb((pl->ns / 2 + pl->col2.np - 1) / pl->col2.np, pl->col2.planes);
-                k_colB_fwd<<<gb, 128, pl->colb_smem, stream>>>(pl->col2, v2, w, ldw, m->d_plane_ptr, m->d_ents);
+                k_colB_fwd<<<gb, pl->colb_threads, pl->colb_smem, stream>>>(pl->col2, v2, w, ldw, m->d_plane_ptr, m->d_ents);
                 D4W_CHECK_LAUNCH("k_colB_fwd");
                 return D4W_OK;
             }
@@ -472,7 +475,7 @@ extern "C" int d4w_fk_apply_pass_ex(d4w_fk_plan* pl, d4w_fk_mask* m, const float
             if (!y) return fail(D4W_ERR_ARG, "d4w_fk_apply: null output");
             if (two && ((uintptr_t)y % 16 == 0)) {
                 dim3 gb((pl->ns / 2 + pl->col2.np - 1) / pl->col2.np, pl->col2.planes);
-                k_colB_inv<<<gb, 128, pl->colb_smem, stream>>>(pl->col2, v2, w, ldw, m->d_plane_ptr, m->d_ents);
+                k_colB_inv<<<gb, pl->colb_threads, pl->colb_smem, stream>>>(pl->col2, v2, w, ldw, m->d_plane_ptr, m->d_ents);
                 D4W_CHECK_LAUNCH("k_colB_inv");
                 dim3 ga((pl->ns / 4 + 127) / 128, pl->col2.x2);
                 switch (pl->col2.x1) {

@@ -18,6 +18,7 @@ struct FkHostPlan {
     std::vector<float2> tw_x2;
     std::vector<int> pos_x2;        // k2 -> position after the level-B forward transform
     size_t colb_smem = 0;
+    int colb_threads = 128;
     FftPlan colpl{}, rowpl{};
     std::vector<float2> tw_col, tw_row, twT;
     std::vector<int> pos2k, k2pos, pos2k_row;
@@ -133,12 +134,17 @@ inline int build_fk_hostplan(int nx, int ns, size_t smem_cap, FkHostPlan& hp, st
             const int x2 = nx / cand;
             if (x2 < 8 || x2 > 1024) continue;
             FftPlan tmp;
-            if (!make_plan(x2, 25, tmp, e2, 128, 8)) continue;
+            const char* bspec = std::getenv("D4W_COLB_PLAN");
+            if (!(bspec && *bspec && make_plan_from_string(x2, bspec, tmp)) && !make_plan(x2, 25, tmp, e2, 160, 8)) continue;
             int np = 8;
             while (np > 1 && (size_t)np * (x2 | 1) * 16 > 56 * 1024) np >>= 1;
             if ((size_t)np * (x2 | 1) * 16 > 100 * 1024) continue;
             hp.two_level = 1; hp.x1 = cand; hp.x2 = x2; hp.planes = cand / 2 + 1; hp.np2 = np; hp.fstride2 = x2 | 1;
             hp.plb = tmp; hp.colb_smem = (size_t)np * hp.fstride2 * 16;
+            int bmax = 1;                                    // most butterflies any stage has per tile
+            for (int st = 0; st < tmp.nstages; ++st) bmax = std::max(bmax, (x2 / tmp.radix[st]) * np);
+            hp.colb_threads = std::min(160, std::max(64, (bmax + 31) / 32 * 32));
+            hp.colb_threads = std::min(160, std::max(32, env_int("D4W_COLB_THREADS", hp.colb_threads)));
             hp.tw_x2 = make_twiddles(x2);
             auto p2k = make_pos2freq(tmp);
             hp.pos_x2.assign((size_t)x2, 0);

@@ -482,6 +482,7 @@ struct Col2Params {
     const float2* twb;       // W_X2^j
     const float2* twn;       // W_nx^j
     int nx, ns, x1, x2, planes, np, fstride;
+    int np_shift;            // np is a power of two
 };
 struct Col2Entry { int pos, slot, flags, pad; };     // flags bit0: conjugate, bit1: stored by the forward pass
 
@@ -544,8 +545,9 @@ __host__ __device__ inline void body_colB_fwd(const Col2Params& cp, const cpd* _
     const int x2 = cp.x2, np = cp.np, hp = cp.ns / 2;
     const int tp0 = tile * np;
     const cpd zero = dmake(vbc(0.f), vbc(0.f));
-    for (int i = tid; i < x2 * np; i += nthr) {
-        const int c2 = i / np, j = i - c2 * np;
+    const int sh = cp.np_shift;
+    for (int i = tid; i < (x2 << sh); i += nthr) {
+        const int c2 = i >> sh, j = i & (np - 1);
         const cpd* src = v2 + ((size_t)plane * x2 + c2) * hp + tp0 + j;
 #ifdef __CUDA_ARCH__
         if (tp0 + j < hp) cp_async16(smem + j * cp.fstride + c2, src); else smem[j * cp.fstride + c2] = zero;
@@ -559,8 +561,8 @@ __host__ __device__ inline void body_colB_fwd(const Col2Params& cp, const cpd* _
     D4W_SYNC();
     fft_forward_stages_dual(smem, cp.plb, cp.twb, np, cp.fstride, tid, nthr);
     const int e0 = plane_ptr[plane], ne = plane_ptr[plane + 1] - e0;
-    for (int i = tid; i < ne * np; i += nthr) {
-        const int ei = i / np, j = i - ei * np;
+    for (int i = tid; i < (ne << sh); i += nthr) {
+        const int ei = i >> sh, j = i & (np - 1);
         const Col2Entry e = ents[e0 + ei];
         if (!(e.flags & 2) || tp0 + j >= hp) continue;
         cpd v = smem[j * cp.fstride + e.pos];
@@ -579,8 +581,9 @@ __host__ __device__ inline void body_colB_inv(const Col2Params& cp, cpd* __restr
     for (int i = tid; i < np * cp.fstride; i += nthr) smem[i] = zero;
     D4W_SYNC();
     const int e0 = plane_ptr[plane], ne = plane_ptr[plane + 1] - e0;
-    for (int i = tid; i < ne * np; i += nthr) {
-        const int ei = i / np, j = i - ei * np;
+    const int sh = cp.np_shift;
+    for (int i = tid; i < (ne << sh); i += nthr) {
+        const int ei = i >> sh, j = i & (np - 1);
         if (tp0 + j >= hp) continue;
         const Col2Entry e = ents[e0 + ei];
         const float4 u = *reinterpret_cast<const float4*>(w + (size_t)e.slot * ldw + 2 * (tp0 + j));
@@ -590,8 +593,8 @@ __host__ __device__ inline void body_colB_inv(const Col2Params& cp, cpd* __restr
     }
     D4W_SYNC();
     fft_inverse_stages_dual(smem, cp.plb, cp.twb, np, cp.fstride, tid, nthr);
-    for (int i = tid; i < x2 * np; i += nthr) {
-        const int c2 = i / np, j = i - c2 * np;
+    for (int i = tid; i < (x2 << sh); i += nthr) {
+        const int c2 = i >> sh, j = i & (np - 1);
         if (tp0 + j < hp) v2[((size_t)plane * x2 + c2) * hp + tp0 + j] = smem[j * cp.fstride + c2];
     }
 }
@@ -884,12 +887,12 @@ k_colA_inv(Col2Params cp, const cpd* __restrict__ v2, float* __restrict__ y) {
     const int t4 = blockIdx.x * blockDim.x + threadIdx.x;
     if (t4 < cp.ns / 4) body_colA_inv<X1>(cp, v2, y, blockIdx.y, t4);
 }
-static __global__ void __launch_bounds__(128, 4)
+static __global__ void __launch_bounds__(160, 3)
 k_colB_fwd(Col2Params cp, const cpd* __restrict__ v2, float2* __restrict__ w, size_t ldw, const int* __restrict__ plane_ptr,
            const Col2Entry* __restrict__ ents) {
     body_colB_fwd(cp, v2, w, ldw, plane_ptr, ents, blockIdx.y, blockIdx.x, threadIdx.x, blockDim.x, reinterpret_cast<cpd*>(d4w_dyn_smem));
 }
-static __global__ void __launch_bounds__(128, 4)
+static __global__ void __launch_bounds__(160, 3)
 k_colB_inv(Col2Params cp, cpd* __restrict__ v2, const float2* __restrict__ w, size_t ldw, const int* __restrict__ plane_ptr,
            const Col2Entry* __restrict__ ents) {
     body_colB_inv(cp, v2, w, ldw, plane_ptr, ents, blockIdx.y, blockIdx.x, threadIdx.x, blockDim.x, reinterpret_cast<cpd*>(d4w_dyn_smem));

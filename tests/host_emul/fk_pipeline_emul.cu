@@ -86,7 +86,7 @@ int main(int argc, char** argv) {
     Col2Params c2p{}; std::vector<cpd> v2; std::vector<int> plane_ptr; std::vector<Col2Entry> ents2;
     if (two) {
         c2p.plb = hp.plb; c2p.twb = hp.tw_x2.data(); c2p.twn = hp.tw_col.data(); c2p.nx = nx; c2p.ns = ns; c2p.x1 = hp.x1; c2p.x2 = hp.x2;
-        c2p.planes = hp.planes; c2p.np = hp.np2; c2p.fstride = hp.fstride2;
+        c2p.planes = hp.planes; c2p.np = hp.np2; c2p.fstride = hp.fstride2; c2p.np_shift = hp.np2 == 8 ? 3 : hp.np2 == 4 ? 2 : hp.np2 == 2 ? 1 : 0;
         v2.resize((size_t)hp.planes * hp.x2 * (ns / 2));
         std::vector<Col2EntryHost> eh; build_col2_entries(hp, k2slot, plane_ptr, eh);
         for (auto& e : eh) ents2.push_back(Col2Entry{e.pos, e.slot, e.flags, 0});
