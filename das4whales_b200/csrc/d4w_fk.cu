@@ -92,6 +92,7 @@ struct d4w_fk_mask {
     int nact = 0;
     std::vector<int> act_k;
     int *d_act_k = nullptr, *d_k2slot = nullptr;
+    int2* d_need = nullptr;
     int2* d_slot_pos = nullptr;
     int* d_plane_ptr = nullptr;
     Col2Entry* d_ents = nullptr;
@@ -253,6 +254,11 @@ static int mask_finish_support(d4w_fk_mask* m, void* stream_v) {
         for (size_t i = 0; i < ents.size(); ++i) dev[i] = Col2Entry{ents[i].pos, ents[i].slot, ents[i].flags, 0};
         D4W_CUDA_TRY(upload(&m->d_plane_ptr, plane_ptr));
         D4W_CUDA_TRY(upload(&m->d_ents, dev));
+        if (pl->hostplan.fused_ra) {
+            std::vector<int2> need;
+            build_col2_need(pl->hostplan, k2slot, need);
+            D4W_CUDA_TRY(upload(&m->d_need, need));
+        }
     }
     return D4W_OK;
 }
@@ -305,7 +311,7 @@ extern "C" int d4w_fk_mask_create_dense(d4w_fk_mask** out, d4w_fk_plan* plan, co
 extern "C" int d4w_fk_mask_destroy(d4w_fk_mask* m) {
     if (!m) return D4W_OK;
     DeviceGuard guard(m->device);
-    cudaFree(m->d_h); cudaFree(m->d_act_k); cudaFree(m->d_k2slot); cudaFree(m->d_slot_pos); cudaFree(m->d_plane_ptr); cudaFree(m->d_ents);
+    cudaFree(m->d_h); cudaFree(m->d_act_k); cudaFree(m->d_k2slot); cudaFree(m->d_slot_pos); cudaFree(m->d_plane_ptr); cudaFree(m->d_ents); cudaFree(m->d_need);
     delete m;
     return D4W_OK;
 }
@@ -374,6 +380,29 @@ static int launch_row_split(const d4w_fk_plan* pl, float2* w, int nact, cudaStre
 //  * passes 1 / 5 run on a time slab [nx][pl->ns] that starts at global sample t_offset (all kept rows);
 //  * passes 2-4 run on `slot_count` kept rows starting at slot `slot_begin` (full time axis), `ws`
 //    pointing at the first local row.
+// fused two-stage level B: (ra, rb) in {16, 20, 25}^2
+template <bool INV, typename V2>
+static bool launch_colB_fused(const d4w_fk_plan* pl, const d4w_fk_mask* m, dim3 gb, V2 v2, float2* w, size_t ldw, cudaStream_t stream) {
+    const int ra = pl->hostplan.fused_ra, rb = pl->hostplan.fused_rb;
+    const size_t smem = (size_t)pl->col2.np * pl->col2.fstride * sizeof(cpd);
+#define D4W_FUSED(RA, RB)                                                                                              \
+    if (ra == RA && rb == RB) {                                                                                        \
+        static bool attr_done = false;   /* opt in to > 48 KB dynamic shared memory once per instantiation */          \
+        if (!attr_done) {                                                                                              \
+            if constexpr (!INV) cudaFuncSetAttribute(k_colB_fwd_fused<RA, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
+            else cudaFuncSetAttribute(k_colB_inv_fused<RA, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);               \
+            attr_done = true;                                                                                          \
+        }                                                                                                              \
+        if constexpr (!INV) k_colB_fwd_fused<RA, RB><<<gb, pl->colb_threads, smem, stream>>>(pl->col2, v2, w, ldw, m->d_need); \
+        else k_colB_inv_fused<RA, RB><<<gb, pl->colb_threads, smem, stream>>>(pl->col2, v2, w, ldw, m->d_need);       \
+        return true;                                                                                                   \
+    }
+    D4W_FUSED(16, 16) D4W_FUSED(16, 20) D4W_FUSED(16, 25) D4W_FUSED(20, 16) D4W_FUSED(20, 20) D4W_FUSED(20, 25)
+    D4W_FUSED(25, 16) D4W_FUSED(25, 20) D4W_FUSED(25, 25)
+#undef D4W_FUSED
+    return false;
+}
+
 extern "C" int d4w_fk_apply_pass_ex(d4w_fk_plan* pl, d4w_fk_mask* m, const float* x, float* y, void* ws, int taper,
                                     int pass, int slot_begin, int slot_count, int t_offset, void* stream_v) {
     if (!pl || !m || !ws) return fail(D4W_ERR_ARG, "d4w_fk_apply: null argument");
@@ -415,7 +444,8 @@ extern "C" int d4w_fk_apply_pass_ex(d4w_fk_plan* pl, d4w_fk_mask* m, const float
                 }
                 D4W_CHECK_LAUNCH("k_colA_fwd");
                 dim3 gb((pl->ns / 2 + pl->col2.np - 1) / pl->col2.np, pl->col2.planes);
-                k_colB_fwd<<<gb, pl->colb_threads, pl->colb_smem, stream>>>(pl->col2, v2, w, ldw, m->d_plane_ptr, m->d_ents);
+                if (!(m->d_need && launch_colB_fused<false>(pl, m, gb, (const cpd*)v2, w, ldw, stream)))
+                    k_colB_fwd<<<gb, pl->colb_threads, pl->colb_smem, stream>>>(pl->col2, v2, w, ldw, m->d_plane_ptr, m->d_ents);
                 D4W_CHECK_LAUNCH("k_colB_fwd");
                 return D4W_OK;
             }
@@ -475,7 +505,8 @@ extern "C" int d4w_fk_apply_pass_ex(d4w_fk_plan* pl, d4w_fk_mask* m, const float
             if (!y) return fail(D4W_ERR_ARG, "d4w_fk_apply: null output");
             if (two && ((uintptr_t)y % 16 == 0)) {
                 dim3 gb((pl->ns / 2 + pl->col2.np - 1) / pl->col2.np, pl->col2.planes);
-                k_colB_inv<<<gb, pl->colb_threads, pl->colb_smem, stream>>>(pl->col2, v2, w, ldw, m->d_plane_ptr, m->d_ents);
+                if (!(m->d_need && launch_colB_fused<true>(pl, m, gb, (cpd*)v2, w, ldw, stream)))
+                    k_colB_inv<<<gb, pl->colb_threads, pl->colb_smem, stream>>>(pl->col2, v2, w, ldw, m->d_plane_ptr, m->d_ents);
                 D4W_CHECK_LAUNCH("k_colB_inv");
                 dim3 ga((pl->ns / 4 + 127) / 128, pl->col2.x2);
                 switch (pl->col2.x1) {

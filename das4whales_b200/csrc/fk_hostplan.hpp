@@ -19,6 +19,7 @@ struct FkHostPlan {
     std::vector<int> pos_x2;        // k2 -> position after the level-B forward transform
     size_t colb_smem = 0;
     int colb_threads = 128;
+    int fused_ra = 0, fused_rb = 0;   // level B as a fused two-stage transform (X2 = ra * rb) when both radices are in {16, 20, 25}
     FftPlan colpl{}, rowpl{};
     std::vector<float2> tw_col, tw_row, twT;
     std::vector<int> pos2k, k2pos, pos2k_row;
@@ -145,6 +146,23 @@ inline int build_fk_hostplan(int nx, int ns, size_t smem_cap, FkHostPlan& hp, st
             for (int st = 0; st < tmp.nstages; ++st) bmax = std::max(bmax, (x2 / tmp.radix[st]) * np);
             hp.colb_threads = std::min(160, std::max(64, (bmax + 31) / 32 * 32));
             hp.colb_threads = std::min(160, std::max(32, env_int("D4W_COLB_THREADS", hp.colb_threads)));
+            if (env_int("D4W_COLB_FUSED", 1)) {
+                // prefer the balanced split (equal item counts in both stages), else the plan's own two radices
+                const int forced_ra = env_int("D4W_COLB_RA", 0);
+                for (int ra : {20, 16, 25}) {
+                    if (forced_ra && ra != forced_ra) continue;
+                    if (x2 % ra) continue;
+                    const int rb = x2 / ra;
+                    if (rb != 16 && rb != 20 && rb != 25) continue;
+                    hp.fused_ra = ra; hp.fused_rb = rb;
+                    break;
+                }
+                if (hp.fused_ra) {
+                    const int items = std::max(hp.fused_ra, hp.fused_rb) * np;
+                    hp.colb_threads = std::min(160, std::max(64, (items + 31) / 32 * 32));
+                    hp.colb_threads = std::min(160, std::max(32, env_int("D4W_COLB_THREADS", hp.colb_threads)));
+                }
+            }
             hp.tw_x2 = make_twiddles(x2);
             auto p2k = make_pos2freq(tmp);
             hp.pos_x2.assign((size_t)x2, 0);
@@ -203,6 +221,27 @@ inline void build_col2_entries(const FkHostPlan& hp, const std::vector<int>& k2s
         }
     }
     plane_ptr[hp.planes] = (int)ents.size();
+}
+
+// dense per-plane table for the fused level-B kernels: need[plane][k2] = (direct slot, mirror slot code)
+inline void build_col2_need(const FkHostPlan& hp, const std::vector<int>& k2slot, std::vector<int2>& need) {
+    const int nx = hp.nx, x1 = hp.x1, x2 = hp.x2;
+    need.assign((size_t)hp.planes * x2, make_int2(-1, -1));
+    auto slot_of = [&](int k) { return (k >= 0 && 2 * k <= nx) ? k2slot[k] : -1; };
+    for (int pl = 0; pl < hp.planes; ++pl) {
+        const bool self = (pl == 0) || (2 * pl == x1);
+        for (int k2 = 0; k2 < x2; ++k2) {
+            int2& e = need[(size_t)pl * x2 + k2];
+            const int k = pl + x1 * k2;
+            if (2 * k <= nx) e.x = slot_of(k);
+            else if (self) { const int sl = slot_of(nx - k); if (sl >= 0) e.y = -2 - sl; }      // inverse only
+        }
+        if (!self)
+            for (int k2 = 0; k2 < x2; ++k2) {
+                const int sl = slot_of((x1 - pl) + x1 * k2);
+                if (sl >= 0) need[(size_t)pl * x2 + (x2 - 1 - k2)].y = sl;
+            }
+    }
 }
 
 }  // namespace d4w

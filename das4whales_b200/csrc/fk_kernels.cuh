@@ -599,6 +599,95 @@ __host__ __device__ inline void body_colB_inv(const Col2Params& cp, cpd* __restr
     }
 }
 
+
+// ------------------------------------------------------------------ fused two-stage level B (X2 = RA * RB)
+// Stage 0 (radix RA over c2 = n + RB*q) runs straight from global memory in registers, stage 1 (radix RB
+// on contiguous groups) writes only the kept wavenumber rows straight to global memory; shared memory is
+// used once, for the transposition between the two stages.  need[plane][k2] = (slot of X[k1' + X1*k2] or -1,
+// slot whose value is conj(P[k2]): >= 0 both directions, <= -2 encodes -2-slot for the inverse only, -1 none).
+template <int RA, int RB>
+__host__ __device__ inline void body_colB_fwd_fused(const Col2Params& cp, const cpd* __restrict__ v2, float2* __restrict__ w,
+                                                    size_t ldw, const int2* __restrict__ need, int plane, int tile, int tid,
+                                                    int nthr, cpd* smem) {
+    const int x2 = cp.x2, np = cp.np, sh = cp.np_shift, hp = cp.ns / 2, fs = cp.fstride;
+    const int tp0 = tile * np;
+    const cpd zero = dmake(vbc(0.f), vbc(0.f));
+    for (int it = tid; it < (RB << sh); it += nthr) {              // item = (n, j)
+        const int n = it >> sh, j = it & (np - 1);
+        const bool ok = tp0 + j < hp;
+        cpd v[RA];
+        const cpd* src = v2 + ((size_t)plane * x2 + n) * hp + tp0 + j;
+        static_for<RA>([&](auto qc) { constexpr int q = decltype(qc)::value; v[q] = ok ? src[(size_t)(RB * q) * hp] : zero; });
+        DFTD<RA, false>::run(v);
+        apply_stage_twiddles<RA, false, true>(v, cp.twb[n]);
+        cpd* dst = smem + j * fs + n;
+        static_for<RA>([&](auto mc) { constexpr int m = decltype(mc)::value; dst[RB * m] = v[outpos<RA>(m)]; });
+    }
+    D4W_SYNC();
+    const int2* nd = need + (size_t)plane * x2;
+    for (int it = tid; it < (RA << sh); it += nthr) {              // item = (group m, j)
+        const int m = it >> sh, j = it & (np - 1);
+        if (tp0 + j >= hp) continue;
+        cpd v[RB];
+        const cpd* src = smem + j * fs + RB * m;
+        static_for<RB>([&](auto ic) { constexpr int i = decltype(ic)::value; v[i] = src[i]; });
+        DFTD<RB, false>::run(v);
+        static_for<RB>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            const int2 e = nd[m + RA * i];
+            const cpd z = v[outpos<RB>(i)];
+            if (e.x >= 0)
+                *reinterpret_cast<float4*>(w + (size_t)e.x * ldw + 2 * (tp0 + j)) = make_float4(f2x_lo(z.x), f2x_lo(z.y), f2x_hi(z.x), f2x_hi(z.y));
+            if (e.y >= 0)
+                *reinterpret_cast<float4*>(w + (size_t)e.y * ldw + 2 * (tp0 + j)) = make_float4(f2x_lo(z.x), -f2x_lo(z.y), f2x_hi(z.x), -f2x_hi(z.y));
+        });
+    }
+}
+
+template <int RA, int RB>
+__host__ __device__ inline void body_colB_inv_fused(const Col2Params& cp, cpd* __restrict__ v2, const float2* __restrict__ w,
+                                                    size_t ldw, const int2* __restrict__ need, int plane, int tile, int tid,
+                                                    int nthr, cpd* smem) {
+    const int x2 = cp.x2, np = cp.np, sh = cp.np_shift, hp = cp.ns / 2, fs = cp.fstride;
+    const int tp0 = tile * np;
+    const cpd zero = dmake(vbc(0.f), vbc(0.f));
+    const int2* nd = need + (size_t)plane * x2;
+    for (int it = tid; it < (RA << sh); it += nthr) {              // item = (group m, j): undo the radix-RB stage
+        const int m = it >> sh, j = it & (np - 1);
+        const bool ok = tp0 + j < hp;
+        cpd v[RB];
+        static_for<RB>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            const int2 e = nd[m + RA * i];
+            const int sd = e.x, sm = (e.y >= 0) ? e.y : ((e.y <= -2) ? -2 - e.y : -1);
+            cpd z = zero;
+            if (ok && sd >= 0) {
+                const float4 u = *reinterpret_cast<const float4*>(w + (size_t)sd * ldw + 2 * (tp0 + j));
+                z = dmake(f2x_set(u.x, u.z), f2x_set(u.y, u.w));
+            } else if (ok && sm >= 0) {
+                const float4 u = *reinterpret_cast<const float4*>(w + (size_t)sm * ldw + 2 * (tp0 + j));
+                z = dmake(f2x_set(u.x, u.z), f2x_set(-u.y, -u.w));
+            }
+            v[i] = z;
+        });
+        DFTD<RB, true>::run(v);
+        cpd* dst = smem + j * fs + RB * m;
+        static_for<RB>([&](auto ic) { constexpr int i = decltype(ic)::value; dst[i] = v[outpos<RB>(i)]; });
+    }
+    D4W_SYNC();
+    for (int it = tid; it < (RB << sh); it += nthr) {              // item = (n, j): undo the radix-RA stage
+        const int n = it >> sh, j = it & (np - 1);
+        if (tp0 + j >= hp) continue;
+        cpd v[RA];
+        const cpd* src = smem + j * fs + n;
+        static_for<RA>([&](auto mc) { constexpr int m = decltype(mc)::value; v[m] = src[RB * m]; });
+        apply_stage_twiddles<RA, true, false>(v, cp.twb[n]);
+        DFTD<RA, true>::run(v);
+        cpd* dst = v2 + ((size_t)plane * x2 + n) * hp + tp0 + j;
+        static_for<RA>([&](auto qc) { constexpr int q = decltype(qc)::value; dst[(size_t)(RB * q) * hp] = v[outpos<RA>(q)]; });
+    }
+}
+
 // ================================================================== __global__ wrappers
 #ifdef __CUDACC__
 extern __shared__ __align__(1024) float2 d4w_dyn_smem[];
@@ -896,6 +985,17 @@ static __global__ void __launch_bounds__(160, 3)
 k_colB_inv(Col2Params cp, cpd* __restrict__ v2, const float2* __restrict__ w, size_t ldw, const int* __restrict__ plane_ptr,
            const Col2Entry* __restrict__ ents) {
     body_colB_inv(cp, v2, w, ldw, plane_ptr, ents, blockIdx.y, blockIdx.x, threadIdx.x, blockDim.x, reinterpret_cast<cpd*>(d4w_dyn_smem));
+}
+
+template <int RA, int RB>
+static __global__ void __launch_bounds__(160, 3)
+k_colB_fwd_fused(Col2Params cp, const cpd* __restrict__ v2, float2* __restrict__ w, size_t ldw, const int2* __restrict__ need) {
+    body_colB_fwd_fused<RA, RB>(cp, v2, w, ldw, need, blockIdx.y, blockIdx.x, threadIdx.x, blockDim.x, reinterpret_cast<cpd*>(d4w_dyn_smem));
+}
+template <int RA, int RB>
+static __global__ void __launch_bounds__(160, 3)
+k_colB_inv_fused(Col2Params cp, cpd* __restrict__ v2, const float2* __restrict__ w, size_t ldw, const int2* __restrict__ need) {
+    body_colB_inv_fused<RA, RB>(cp, v2, w, ldw, need, blockIdx.y, blockIdx.x, threadIdx.x, blockDim.x, reinterpret_cast<cpd*>(d4w_dyn_smem));
 }
 
 static __global__ void k_mask_rowmax(MaskParams mp, unsigned int* rowmax, int fchunk) {

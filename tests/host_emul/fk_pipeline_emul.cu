@@ -42,6 +42,20 @@ static void split_dispatch(int t1, bool inv, float2* w, size_t ldw, int t2, cons
     }
 }
 
+template <bool INV>
+static bool colB_fused_emul(const FkHostPlan& hp, const Col2Params& c2p, cpd* v2, float2* w, size_t ldw, const int2* need, int pl, int tb, cpd* smem) {
+#define EM_FUSED(RA, RB)                                                                                     \
+    if (hp.fused_ra == RA && hp.fused_rb == RB) {                                                            \
+        if constexpr (!INV) body_colB_fwd_fused<RA, RB>(c2p, v2, w, ldw, need, pl, tb, 0, 1, smem);          \
+        else body_colB_inv_fused<RA, RB>(c2p, v2, w, ldw, need, pl, tb, 0, 1, smem);                         \
+        return true;                                                                                         \
+    }
+    EM_FUSED(16, 16) EM_FUSED(16, 20) EM_FUSED(16, 25) EM_FUSED(20, 16) EM_FUSED(20, 20) EM_FUSED(20, 25)
+    EM_FUSED(25, 16) EM_FUSED(25, 20) EM_FUSED(25, 25)
+#undef EM_FUSED
+    return false;
+}
+
 int main(int argc, char** argv) {
     if (argc < 3) return 2;
     FILE* fi = fopen(argv[1], "rb");
@@ -83,7 +97,7 @@ int main(int argc, char** argv) {
     const size_t ldw = ns;
     const int tile = 2 * hp.nc, ntiles = (ns + tile - 1) / tile;
     const bool two = hp.two_level && nact > 0;
-    Col2Params c2p{}; std::vector<cpd> v2; std::vector<int> plane_ptr; std::vector<Col2Entry> ents2;
+    Col2Params c2p{}; std::vector<int2> need2; std::vector<cpd> v2; std::vector<int> plane_ptr; std::vector<Col2Entry> ents2;
     if (two) {
         c2p.plb = hp.plb; c2p.twb = hp.tw_x2.data(); c2p.twn = hp.tw_col.data(); c2p.nx = nx; c2p.ns = ns; c2p.x1 = hp.x1; c2p.x2 = hp.x2;
         c2p.planes = hp.planes; c2p.np = hp.np2; c2p.fstride = hp.fstride2; c2p.np_shift = hp.np2 == 8 ? 3 : hp.np2 == 4 ? 2 : hp.np2 == 2 ? 1 : 0;
@@ -91,11 +105,13 @@ int main(int argc, char** argv) {
         std::vector<Col2EntryHost> eh; build_col2_entries(hp, k2slot, plane_ptr, eh);
         for (auto& e : eh) ents2.push_back(Col2Entry{e.pos, e.slot, e.flags, 0});
         smem.resize(std::max(smem.size(), hp.colb_smem / sizeof(float2) + 16));
+        if (hp.fused_ra) build_col2_need(hp, k2slot, need2);
         colA_dispatch(false, c2p, x.data(), v2.data(), nullptr, taper ? hp.taper.data() : nullptr);
         const int ntb = (ns / 2 + hp.np2 - 1) / hp.np2;
         for (int pl = 0; pl < hp.planes; ++pl)
             for (int tb = 0; tb < ntb; ++tb)
-                body_colB_fwd(c2p, v2.data(), w.data(), ldw, plane_ptr.data(), ents2.data(), pl, tb, 0, 1, reinterpret_cast<cpd*>(smem.data()));
+                if (!(hp.fused_ra && colB_fused_emul<false>(hp, c2p, v2.data(), w.data(), ldw, need2.data(), pl, tb, reinterpret_cast<cpd*>(smem.data()))))
+                    body_colB_fwd(c2p, v2.data(), w.data(), ldw, plane_ptr.data(), ents2.data(), pl, tb, 0, 1, reinterpret_cast<cpd*>(smem.data()));
     }
     if (nact && !two)
         for (int b = 0; b < ntiles; ++b) {
@@ -116,7 +132,8 @@ int main(int argc, char** argv) {
         const int ntb = (ns / 2 + hp.np2 - 1) / hp.np2;
         for (int pl = 0; pl < hp.planes; ++pl)
             for (int tb = 0; tb < ntb; ++tb)
-                body_colB_inv(c2p, v2.data(), w.data(), ldw, plane_ptr.data(), ents2.data(), pl, tb, 0, 1, reinterpret_cast<cpd*>(smem.data()));
+                if (!(hp.fused_ra && colB_fused_emul<true>(hp, c2p, v2.data(), w.data(), ldw, need2.data(), pl, tb, reinterpret_cast<cpd*>(smem.data()))))
+                    body_colB_inv(c2p, v2.data(), w.data(), ldw, plane_ptr.data(), ents2.data(), pl, tb, 0, 1, reinterpret_cast<cpd*>(smem.data()));
         colA_dispatch(true, c2p, nullptr, v2.data(), y.data(), nullptr);
     }
     for (int b = 0; b < ntiles && !two; ++b) {
@@ -127,7 +144,7 @@ int main(int argc, char** argv) {
     FILE* fo = fopen(argv[2], "wb");
     fwrite(y.data(), 4, y.size(), fo);
     fwrite(&nact, 4, 1, fo);
-    int info[4] = {hp.t1, hp.t2, hp.nc, hp.two_level ? 1000 + hp.x1 : (hp.dual ? 100 + hp.colpl.nstages : hp.colpl.nstages)};
+    int info[4] = {hp.t1, hp.t2, hp.nc, hp.two_level ? 1000 * (1 + hp.fused_ra) + hp.x1 : (hp.dual ? 100 + hp.colpl.nstages : hp.colpl.nstages)};
     fwrite(info, 4, 4, fo);
     fclose(fo);
     return 0;

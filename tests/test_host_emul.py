@@ -59,7 +59,10 @@ def _run(exe, tmp, nx, ns, kind, taper, x, kval, fval, c, H=None, dense=None, co
 CASES = [(40, 240, 1, False, None), (45, 175, 1, True, None), (38, 120, 2, False, None),
          (100, 1200, 1, True, {"D4W_T1": "12"}), (30, 600, 1, False, {"D4W_T1": "5", "D4W_COL_NC": "1"}),
          (250, 360, 1, False, {"D4W_T1": "6", "D4W_COL_NC": "4"}),
-         (10000, 16, 1, False, None),      # the bench column plan (two-level 25 x 400)
+         (10000, 16, 1, False, None),      # the bench column plan (two-level 25 x 400, fused 20 x 20 level B)
+         (10000, 10, 1, True, {"D4W_COLB_RA": "16"}), (10000, 8, 1, False, {"D4W_COLB_RA": "25"}),
+         (10000, 8, 1, False, {"D4W_COLB_FUSED": "0"}),      # shared-memory engine level B
+         (6400, 12, 1, False, {"D4W_COL_X1": "16"}), (8000, 8, 1, True, {"D4W_COL_X1": "20"}),
          (10000, 8, 1, False, {"D4W_COL_TWO_LEVEL": "0"}),   # single-level dual column kernels (20x20x25)
          (400, 24, 1, True, None), (320, 12, 1, True, {"D4W_COL_X1": "16"}), (500, 16, 1, False, {"D4W_COL_X1": "20"})]
 
