@@ -78,6 +78,7 @@ struct d4w_fk_plan {
     float2* d_tw_x2 = nullptr;
     size_t colb_smem = 0;
     int colb_threads = 128;
+    PipeParams pipe{};                        // pipe.nchunks > 0: single-launch pipelined level A+B
     FkHostPlan hostplan;                      // kept for mask-time table building
     std::vector<int> h_k2pos;
     int col_threads = 256, row_threads = 256;
@@ -176,6 +177,17 @@ extern "C" int d4w_fk_plan_create(d4w_fk_plan** out, int nx, int ns, int device)
         pl->col2.np = hp.np2; pl->col2.fstride = hp.fstride2;
         pl->col2.np_shift = hp.np2 == 8 ? 3 : hp.np2 == 4 ? 2 : hp.np2 == 2 ? 1 : 0;
         pl->colb_threads = hp.colb_threads;
+        pl->col2.vhp = hp.chunk_pairs; pl->col2.tpb = 0; pl->col2.tpn = hp.chunk_pairs;
+        if (hp.pipe) {
+            PipeParams& pp = pl->pipe;
+            pp.nchunks = (ns / 2 + hp.chunk_pairs - 1) / hp.chunk_pairs;
+            pp.lag = hp.pipe_lag; pp.nbuf = hp.pipe_lag + std::max(2, env_int("D4W_PIPE_SLACK", 2));
+            pp.cq = hp.pipe_cq; pp.rpc = 160 / hp.pipe_cq;
+            pp.nA = (hp.x2 + pp.rpc - 1) / pp.rpc;
+            pp.tiles = hp.chunk_pairs / hp.np2; pp.nB = hp.planes * pp.tiles;
+            pp.hints = env_int("D4W_PIPE_HINTS", 1);
+            pp.vbuf_elems = (size_t)hp.planes * hp.x2 * hp.chunk_pairs;
+        }
         cudaFuncSetAttribute(k_colB_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
         cudaFuncSetAttribute(k_colB_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
     }
@@ -356,7 +368,11 @@ extern "C" size_t d4w_fk_workspace_bytes(const d4w_fk_plan* pl, const d4w_fk_mas
     if (!pl || !m) return 0;
     size_t b = std::max<size_t>((size_t)m->nact * pl->ns * sizeof(float2), 16);
     b = (b + 255) / 256 * 256;
-    if (pl->two_level) b += (size_t)pl->col2.planes * pl->col2.x2 * pl->ns * sizeof(float2);     // level-A/B intermediate V
+    if (pl->two_level) {
+        const int nbuf = pl->pipe.nchunks ? pl->pipe.nbuf : 1;
+        b += (size_t)nbuf * pl->col2.planes * pl->col2.x2 * pl->col2.vhp * sizeof(cpd);     // level-A/B intermediate V (chunk ring)
+        if (pl->pipe.nchunks) b += (size_t)(2 * pl->pipe.nchunks + 1 + 63) / 64 * 64 * sizeof(unsigned);   // ticket + chunk counters
+    }
     return b;
 }
 
@@ -382,7 +398,7 @@ static int launch_row_split(const d4w_fk_plan* pl, float2* w, int nact, cudaStre
 //    pointing at the first local row.
 // fused two-stage level B: (ra, rb) in {16, 20, 25}^2
 template <bool INV, typename V2>
-static bool launch_colB_fused(const d4w_fk_plan* pl, const d4w_fk_mask* m, dim3 gb, V2 v2, float2* w, size_t ldw, cudaStream_t stream) {
+static bool launch_colB_fused(const d4w_fk_plan* pl, const Col2Params& c2, const d4w_fk_mask* m, dim3 gb, V2 v2, float2* w, size_t ldw, cudaStream_t stream) {
     const int ra = pl->hostplan.fused_ra, rb = pl->hostplan.fused_rb;
     const size_t smem = (size_t)pl->col2.np * pl->col2.fstride * sizeof(cpd);
 #define D4W_FUSED(RA, RB)                                                                                              \
@@ -393,14 +409,40 @@ static bool launch_colB_fused(const d4w_fk_plan* pl, const d4w_fk_mask* m, dim3 
             else cudaFuncSetAttribute(k_colB_inv_fused<RA, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);               \
             attr_done = true;                                                                                          \
         }                                                                                                              \
-        if constexpr (!INV) k_colB_fwd_fused<RA, RB><<<gb, pl->colb_threads, smem, stream>>>(pl->col2, v2, w, ldw, m->d_need); \
-        else k_colB_inv_fused<RA, RB><<<gb, pl->colb_threads, smem, stream>>>(pl->col2, v2, w, ldw, m->d_need);       \
+        if constexpr (!INV) k_colB_fwd_fused<RA, RB><<<gb, pl->colb_threads, smem, stream>>>(c2, v2, w, ldw, m->d_need); \
+        else k_colB_inv_fused<RA, RB><<<gb, pl->colb_threads, smem, stream>>>(c2, v2, w, ldw, m->d_need);       \
         return true;                                                                                                   \
     }
     D4W_FUSED(16, 16) D4W_FUSED(16, 20) D4W_FUSED(16, 25) D4W_FUSED(20, 16) D4W_FUSED(20, 20) D4W_FUSED(20, 25)
     D4W_FUSED(25, 16) D4W_FUSED(25, 20) D4W_FUSED(25, 25)
 #undef D4W_FUSED
     return false;
+}
+
+// single-launch pipelined level A + level B (forward: x -> kept rows W; inverse: W -> y)
+template <bool INV>
+static int launch_col2_pipe(const d4w_fk_plan* pl, const d4w_fk_mask* m, const float* x, float* y, cpd* v2, float2* w, size_t ldw,
+                            const float* tap, cudaStream_t stream) {
+    PipeParams pp = pl->pipe;
+    pp.cnt = reinterpret_cast<unsigned*>(v2 + (size_t)pp.nbuf * pp.vbuf_elems);
+    cudaError_t e = cudaMemsetAsync(pp.cnt, 0, (size_t)(2 * pp.nchunks + 1) * sizeof(unsigned), stream);
+    if (e != cudaSuccess) return fail(D4W_ERR_CUDA, std::string("pipe counters: ") + cudaGetErrorString(e));
+    const size_t smem = (size_t)pl->col2.np * pl->col2.fstride * sizeof(cpd);
+    const unsigned grid = (unsigned)(pp.nchunks + pp.lag) * (unsigned)(pp.nA + pp.nB);
+    const int ra = pl->hostplan.fused_ra, x1 = pl->col2.x1;
+    bool done = false;
+#define D4W_PIPE(X1, RA, RB)                                                                                              \
+    if (!done && x1 == X1 && ra == RA) {                                                                                  \
+        static bool attr_done = false;                                                                                    \
+        if (!attr_done) { cudaFuncSetAttribute(k_col2_pipe<X1, RA, RB, INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_done = true; } \
+        k_col2_pipe<X1, RA, RB, INV><<<grid, 160, smem, stream>>>(pl->col2, pp, x, y, v2, w, ldw, m->d_need, tap);        \
+        done = true;                                                                                                      \
+    }
+    D4W_PIPE(25, 20, 20) D4W_PIPE(25, 16, 25) D4W_PIPE(20, 20, 20) D4W_PIPE(20, 16, 25) D4W_PIPE(16, 20, 20) D4W_PIPE(16, 16, 25)
+#undef D4W_PIPE
+    if (!done) return fail(D4W_ERR_UNSUPPORTED, "pipelined column kernel: unsupported split");
+    D4W_CHECK_LAUNCH("k_col2_pipe");
+    return D4W_OK;
 }
 
 extern "C" int d4w_fk_apply_pass_ex(d4w_fk_plan* pl, d4w_fk_mask* m, const float* x, float* y, void* ws, int taper,
@@ -436,17 +478,22 @@ extern "C" int d4w_fk_apply_pass_ex(d4w_fk_plan* pl, d4w_fk_mask* m, const float
             if (!x) return fail(D4W_ERR_ARG, "d4w_fk_apply: null input");
             if (nact == 0) return D4W_OK;
             if (two && ((uintptr_t)x % 16 == 0)) {
-                dim3 ga((pl->ns / 4 + 127) / 128, pl->col2.x2);
-                switch (pl->col2.x1) {
-                    case 25: k_colA_fwd<25><<<ga, 128, 0, stream>>>(pl->col2, x, v2, tap); break;
-                    case 20: k_colA_fwd<20><<<ga, 128, 0, stream>>>(pl->col2, x, v2, tap); break;
-                    default: k_colA_fwd<16><<<ga, 128, 0, stream>>>(pl->col2, x, v2, tap); break;
+                if (pl->pipe.nchunks && m->d_need) return launch_col2_pipe<false>(pl, m, x, nullptr, v2, w, ldw, tap, stream);
+                for (int tpb = 0; tpb < pl->ns / 2; tpb += pl->col2.vhp) {        // time chunks: V stays in L2 from A to B
+                    Col2Params c2 = pl->col2;
+                    c2.tpb = tpb; c2.tpn = std::min(c2.vhp, pl->ns / 2 - tpb);
+                    dim3 ga((c2.tpn / 2 + 127) / 128, c2.x2);
+                    switch (c2.x1) {
+                        case 25: k_colA_fwd<25><<<ga, 128, 0, stream>>>(c2, x, v2, tap); break;
+                        case 20: k_colA_fwd<20><<<ga, 128, 0, stream>>>(c2, x, v2, tap); break;
+                        default: k_colA_fwd<16><<<ga, 128, 0, stream>>>(c2, x, v2, tap); break;
+                    }
+                    D4W_CHECK_LAUNCH("k_colA_fwd");
+                    dim3 gb((c2.tpn + c2.np - 1) / c2.np, c2.planes);
+                    if (!(m->d_need && launch_colB_fused<false>(pl, c2, m, gb, (const cpd*)v2, w, ldw, stream)))
+                        k_colB_fwd<<<gb, pl->colb_threads, pl->colb_smem, stream>>>(c2, v2, w, ldw, m->d_plane_ptr, m->d_ents);
+                    D4W_CHECK_LAUNCH("k_colB_fwd");
                 }
-                D4W_CHECK_LAUNCH("k_colA_fwd");
-                dim3 gb((pl->ns / 2 + pl->col2.np - 1) / pl->col2.np, pl->col2.planes);
-                if (!(m->d_need && launch_colB_fused<false>(pl, m, gb, (const cpd*)v2, w, ldw, stream)))
-                    k_colB_fwd<<<gb, pl->colb_threads, pl->colb_smem, stream>>>(pl->col2, v2, w, ldw, m->d_plane_ptr, m->d_ents);
-                D4W_CHECK_LAUNCH("k_colB_fwd");
                 return D4W_OK;
             }
             if (pl->col.tma && ((uintptr_t)x % 16 == 0)) {
@@ -504,17 +551,22 @@ extern "C" int d4w_fk_apply_pass_ex(d4w_fk_plan* pl, d4w_fk_mask* m, const float
         case 5:
             if (!y) return fail(D4W_ERR_ARG, "d4w_fk_apply: null output");
             if (two && ((uintptr_t)y % 16 == 0)) {
-                dim3 gb((pl->ns / 2 + pl->col2.np - 1) / pl->col2.np, pl->col2.planes);
-                if (!(m->d_need && launch_colB_fused<true>(pl, m, gb, (cpd*)v2, w, ldw, stream)))
-                    k_colB_inv<<<gb, pl->colb_threads, pl->colb_smem, stream>>>(pl->col2, v2, w, ldw, m->d_plane_ptr, m->d_ents);
-                D4W_CHECK_LAUNCH("k_colB_inv");
-                dim3 ga((pl->ns / 4 + 127) / 128, pl->col2.x2);
-                switch (pl->col2.x1) {
-                    case 25: k_colA_inv<25><<<ga, 128, 0, stream>>>(pl->col2, v2, y); break;
-                    case 20: k_colA_inv<20><<<ga, 128, 0, stream>>>(pl->col2, v2, y); break;
-                    default: k_colA_inv<16><<<ga, 128, 0, stream>>>(pl->col2, v2, y); break;
+                if (pl->pipe.nchunks && m->d_need) return launch_col2_pipe<true>(pl, m, nullptr, y, v2, w, ldw, nullptr, stream);
+                for (int tpb = 0; tpb < pl->ns / 2; tpb += pl->col2.vhp) {
+                    Col2Params c2 = pl->col2;
+                    c2.tpb = tpb; c2.tpn = std::min(c2.vhp, pl->ns / 2 - tpb);
+                    dim3 gb((c2.tpn + c2.np - 1) / c2.np, c2.planes);
+                    if (!(m->d_need && launch_colB_fused<true>(pl, c2, m, gb, (cpd*)v2, w, ldw, stream)))
+                        k_colB_inv<<<gb, pl->colb_threads, pl->colb_smem, stream>>>(c2, v2, w, ldw, m->d_plane_ptr, m->d_ents);
+                    D4W_CHECK_LAUNCH("k_colB_inv");
+                    dim3 ga((c2.tpn / 2 + 127) / 128, c2.x2);
+                    switch (c2.x1) {
+                        case 25: k_colA_inv<25><<<ga, 128, 0, stream>>>(c2, v2, y); break;
+                        case 20: k_colA_inv<20><<<ga, 128, 0, stream>>>(c2, v2, y); break;
+                        default: k_colA_inv<16><<<ga, 128, 0, stream>>>(c2, v2, y); break;
+                    }
+                    D4W_CHECK_LAUNCH("k_colA_inv");
                 }
-                D4W_CHECK_LAUNCH("k_colA_inv");
                 return D4W_OK;
             }
             if (pl->col.tma && ((uintptr_t)y % 16 == 0)) {

@@ -19,6 +19,8 @@ struct FkHostPlan {
     std::vector<int> pos_x2;        // k2 -> position after the level-B forward transform
     size_t colb_smem = 0;
     int colb_threads = 128;
+    int pipe = 0, pipe_lag = 2, pipe_cq = 80;   // single-launch pipelined level A+B (V ring resident in L2)
+    int chunk_pairs = 0;              // sample pairs per level-A/level-B launch pair (V chunk sized to stay in L2)
     int fused_ra = 0, fused_rb = 0;   // level B as a fused two-stage transform (X2 = ra * rb) when both radices are in {16, 20, 25}
     FftPlan colpl{}, rowpl{};
     std::vector<float2> tw_col, tw_row, twT;
@@ -146,6 +148,16 @@ inline int build_fk_hostplan(int nx, int ns, size_t smem_cap, FkHostPlan& hp, st
             for (int st = 0; st < tmp.nstages; ++st) bmax = std::max(bmax, (x2 / tmp.radix[st]) * np);
             hp.colb_threads = std::min(160, std::max(64, (bmax + 31) / 32 * 32));
             hp.colb_threads = std::min(160, std::max(32, env_int("D4W_COLB_THREADS", hp.colb_threads)));
+            {
+                // V chunk = planes * x2 * pairs * 16 B; keep it well inside the 126 MB L2 (D4W_COL_CHUNK_MB = 0: one chunk)
+                const int mb = env_int("D4W_COL_CHUNK_MB", 40);
+                const long long per_pair = (long long)hp.planes * x2 * 16;
+                long long pairs = mb > 0 ? (long long)mb * 1000000 / per_pair / 256 * 256 : (long long)ns / 2;
+                pairs = std::max<long long>(pairs, 256);
+                const int forced = env_int("D4W_COL_CHUNK_PAIRS", 0);           // test knob; multiple of 8
+                if (forced > 0) pairs = std::max(8, forced / 8 * 8);
+                hp.chunk_pairs = (int)std::min<long long>(pairs, ns / 2);
+            }
             if (env_int("D4W_COLB_FUSED", 1)) {
                 // prefer the balanced split (equal item counts in both stages), else the plan's own two radices
                 const int forced_ra = env_int("D4W_COLB_RA", 0);
@@ -162,6 +174,15 @@ inline int build_fk_hostplan(int nx, int ns, size_t smem_cap, FkHostPlan& hp, st
                     hp.colb_threads = std::min(160, std::max(64, (items + 31) / 32 * 32));
                     hp.colb_threads = std::min(160, std::max(32, env_int("D4W_COLB_THREADS", hp.colb_threads)));
                 }
+            }
+            // pipelined single launch: needs the fused level B with (ra, rb) in {(20,20), (16,25)} and 8-pair tiles
+            if (env_int("D4W_COL_PIPE", 1) && hp.fused_ra && np == 8 &&
+                ((hp.fused_ra == 20 && hp.fused_rb == 20) || (hp.fused_ra == 16 && hp.fused_rb == 25))) {
+                int cq = env_int("D4W_PIPE_CQ", 80);
+                if (cq < 4 || 160 % cq || (2 * cq) % np) cq = 80;                // strip width in quads; 160 threads = cq x rpc
+                hp.pipe = 1; hp.pipe_cq = cq; hp.chunk_pairs = 2 * cq;
+                hp.pipe_lag = std::min(256, std::max(1, env_int("D4W_PIPE_LAG", 2)));
+                hp.colb_threads = 160;
             }
             hp.tw_x2 = make_twiddles(x2);
             auto p2k = make_pos2freq(tmp);

@@ -483,20 +483,77 @@ struct Col2Params {
     const float2* twn;       // W_nx^j
     int nx, ns, x1, x2, planes, np, fstride;
     int np_shift;            // np is a power of two
+    // time chunk handled by one level-A/level-B launch pair: sample pairs [tpb, tpb + tpn) of the record; the
+    // intermediate V holds just this chunk (row stride vhp pairs) so that it stays resident in L2 between the two
+    int vhp, tpb, tpn;
 };
+
+// ---- global-memory access with an L2 eviction policy (pipelined level A/B kernel) -------------------------------
+// `keep` (evict_last) is used for the chunk ring of the intermediate V, which must survive in L2 from its producer
+// CTA to its consumer CTA; `stream` (evict_first) for data touched once (x, y, the kept rows W).  V is read with
+// .cg so that a re-used ring slot can never be served from a stale L1 line.
+struct L2Pol { unsigned long long keep, stream; };
+#ifdef __CUDACC__
+__device__ __forceinline__ L2Pol make_l2pol(bool hints) {
+    L2Pol p;
+    if (hints) {
+        asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p.keep));
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p.stream));
+    } else {
+        asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p.keep));
+        p.stream = p.keep;
+    }
+    return p;
+}
+__device__ __forceinline__ float4 ldg16_pol(const void* p, unsigned long long pol) {
+    float4 r;
+    asm volatile("ld.global.cg.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p), "l"(pol) : "memory");
+    return r;
+}
+__device__ __forceinline__ void stg16_pol(void* p, float4 v, unsigned long long pol) {
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+}
+#endif
+template <bool PIPE> D4W_HD float4 ld16(const void* p, unsigned long long pol) {
+#ifdef __CUDA_ARCH__
+    if constexpr (PIPE) return ldg16_pol(p, pol);
+#endif
+    (void)pol;
+    return *reinterpret_cast<const float4*>(p);
+}
+template <bool PIPE> D4W_HD void st16(void* p, float4 v, unsigned long long pol) {
+#ifdef __CUDA_ARCH__
+    if constexpr (PIPE) { stg16_pol(p, v, pol); return; }
+#endif
+    (void)pol;
+    *reinterpret_cast<float4*>(p) = v;
+}
+template <bool PIPE> D4W_HD cpd ldc(const cpd* p, unsigned long long pol) {
+    const float4 u = ld16<PIPE>(p, pol);
+    return dmake(f2x_set(u.x, u.y), f2x_set(u.z, u.w));
+}
+template <bool PIPE> D4W_HD void stc(cpd* p, cpd z, unsigned long long pol) {
+    st16<PIPE>(p, make_float4(f2x_lo(z.x), f2x_hi(z.x), f2x_lo(z.y), f2x_hi(z.y)), pol);
+}
+
 struct Col2Entry { int pos, slot, flags, pad; };     // flags bit0: conjugate, bit1: stored by the forward pass
 
-template <int X1>
+template <int X1, bool PIPE = false>
 __host__ __device__ inline void body_colA_fwd(const Col2Params& cp, const float* __restrict__ x, cpd* __restrict__ v2,
-                                              const float* __restrict__ taper, int c2, int t4) {
+                                              const float* __restrict__ taper, int c2, int t4, int tpb, L2Pol pol = L2Pol{0, 0}) {
     const int ns = cp.ns, x2 = cp.x2;
-    const size_t hp = (size_t)(ns / 2);
+    const size_t hp = (size_t)cp.vhp;
+    const size_t tg = 4 * (size_t)(tpb / 2 + t4);      // first of this thread's four samples in the record
     cpd v[X1];
     f2x ta = vbc(1.f), tb = vbc(1.f);
-    if (taper) { ta = f2x_set(taper[4 * t4], taper[4 * t4 + 1]); tb = f2x_set(taper[4 * t4 + 2], taper[4 * t4 + 3]); }
+    if (taper) { ta = f2x_set(taper[tg], taper[tg + 1]); tb = f2x_set(taper[tg + 2], taper[tg + 3]); }
+    float2 twp[X1 / 2 + 1];                                          // W_nx^{c2 k1}, k1 = 0 .. X1/2, from one table read
+    twiddle_powers<X1 / 2 + 1>(cp.twn[c2], twp);
     static_for<X1>([&](auto c1c) {
         constexpr int c1 = decltype(c1c)::value;
-        const float4 a = *reinterpret_cast<const float4*>(x + (size_t)(x2 * c1 + c2) * ns + 4 * t4);
+        const float4 a = ld16<PIPE>(x + (size_t)(x2 * c1 + c2) * ns + tg, pol.stream);
         v[c1] = dmake(f2x_set(a.x, a.y), f2x_set(a.z, a.w));
         if (taper) { v[c1].x = vmul(v[c1].x, ta); v[c1].y = vmul(v[c1].y, tb); }
     });
@@ -507,22 +564,25 @@ __host__ __device__ inline void body_colA_fwd(const Col2Params& cp, const float*
         const cpd z = v[outpos<X1>(k1)], z2 = v[outpos<X1>((X1 - k1) % X1)];
         cpd fa = dmake(vmul(vadd(z.x, z2.x), half), vmul(vsub(z.y, z2.y), half));     // lanes F_t, F_t+1
         cpd fb = dmake(vmul(vadd(z.y, z2.y), half), vmul(vsub(z2.x, z.x), half));     // lanes F_t+2, F_t+3
-        if (k1 > 0) { const float2 w = cp.twn[c2 * k1]; fa = dmul_s(fa, w); fb = dmul_s(fb, w); }
+        if (k1 > 0) { const float2 w = twp[k1]; fa = dmul_s(fa, w); fb = dmul_s(fb, w); }
         cpd* o = v2 + ((size_t)k1 * x2 + c2) * hp + 2 * t4;
-        o[0] = fa; o[1] = fb;
+        stc<PIPE>(o, fa, pol.keep); stc<PIPE>(o + 1, fb, pol.keep);
     });
 }
-
-template <int X1>
-__host__ __device__ inline void body_colA_inv(const Col2Params& cp, const cpd* __restrict__ v2, float* __restrict__ y, int c2, int t4) {
+template <int X1, bool PIPE = false>
+__host__ __device__ inline void body_colA_inv(const Col2Params& cp, const cpd* __restrict__ v2, float* __restrict__ y, int c2, int t4,
+                                              int tpb, L2Pol pol = L2Pol{0, 0}) {
     const int ns = cp.ns, x2 = cp.x2;
-    const size_t hp = (size_t)(ns / 2);
+    const size_t hp = (size_t)cp.vhp;
+    const size_t tg = 4 * (size_t)(tpb / 2 + t4);
     cpd v[X1];
+    float2 twp[X1 / 2 + 1];
+    twiddle_powers<X1 / 2 + 1>(cp.twn[c2], twp);
     static_for<X1 / 2 + 1>([&](auto kc) {
         constexpr int k1 = decltype(kc)::value;
         const cpd* in = v2 + ((size_t)k1 * x2 + c2) * hp + 2 * t4;
-        cpd fa = in[0], fb = in[1];
-        if (k1 > 0) { const float2 w = cp.twn[c2 * k1]; fa = dmulc_s(fa, w); fb = dmulc_s(fb, w); }
+        cpd fa = ldc<PIPE>(in, pol.keep), fb = ldc<PIPE>(in + 1, pol.keep);
+        if (k1 > 0) { const float2 w = twp[k1]; fa = dmulc_s(fa, w); fb = dmulc_s(fb, w); }
         if (k1 == 0 || 2 * k1 == X1) {                       // self-conjugate in k1: real
             v[k1] = dmake(fa.x, fb.x);
         } else {
@@ -534,7 +594,7 @@ __host__ __device__ inline void body_colA_inv(const Col2Params& cp, const cpd* _
     static_for<X1>([&](auto c1c) {
         constexpr int c1 = decltype(c1c)::value;
         const cpd z = v[outpos<X1>(c1)];
-        *reinterpret_cast<float4*>(y + (size_t)(x2 * c1 + c2) * ns + 4 * t4) = make_float4(f2x_lo(z.x), f2x_hi(z.x), f2x_lo(z.y), f2x_hi(z.y));
+        st16<PIPE>(y + (size_t)(x2 * c1 + c2) * ns + tg, make_float4(f2x_lo(z.x), f2x_hi(z.x), f2x_lo(z.y), f2x_hi(z.y)), pol.stream);
     });
 }
 
@@ -542,7 +602,7 @@ __host__ __device__ inline void body_colA_inv(const Col2Params& cp, const cpd* _
 __host__ __device__ inline void body_colB_fwd(const Col2Params& cp, const cpd* __restrict__ v2, float2* __restrict__ w, size_t ldw,
                                               const int* __restrict__ plane_ptr, const Col2Entry* __restrict__ ents, int plane,
                                               int tile, int tid, int nthr, cpd* smem) {
-    const int x2 = cp.x2, np = cp.np, hp = cp.ns / 2;
+    const int x2 = cp.x2, np = cp.np, hp = cp.vhp, tpn = cp.tpn;
     const int tp0 = tile * np;
     const cpd zero = dmake(vbc(0.f), vbc(0.f));
     const int sh = cp.np_shift;
@@ -550,9 +610,9 @@ __host__ __device__ inline void body_colB_fwd(const Col2Params& cp, const cpd* _
         const int c2 = i >> sh, j = i & (np - 1);
         const cpd* src = v2 + ((size_t)plane * x2 + c2) * hp + tp0 + j;
 #ifdef __CUDA_ARCH__
-        if (tp0 + j < hp) cp_async16(smem + j * cp.fstride + c2, src); else smem[j * cp.fstride + c2] = zero;
+        if (tp0 + j < tpn) cp_async16(smem + j * cp.fstride + c2, src); else smem[j * cp.fstride + c2] = zero;
 #else
-        smem[j * cp.fstride + c2] = (tp0 + j < hp) ? *src : zero;
+        smem[j * cp.fstride + c2] = (tp0 + j < tpn) ? *src : zero;
 #endif
     }
 #ifdef __CUDA_ARCH__
@@ -564,10 +624,10 @@ __host__ __device__ inline void body_colB_fwd(const Col2Params& cp, const cpd* _
     for (int i = tid; i < (ne << sh); i += nthr) {
         const int ei = i >> sh, j = i & (np - 1);
         const Col2Entry e = ents[e0 + ei];
-        if (!(e.flags & 2) || tp0 + j >= hp) continue;
+        if (!(e.flags & 2) || tp0 + j >= tpn) continue;
         cpd v = smem[j * cp.fstride + e.pos];
         if (e.flags & 1) v.y = vneg(v.y);
-        *reinterpret_cast<float4*>(w + (size_t)e.slot * ldw + 2 * (tp0 + j)) = make_float4(f2x_lo(v.x), f2x_lo(v.y), f2x_hi(v.x), f2x_hi(v.y));
+        *reinterpret_cast<float4*>(w + (size_t)e.slot * ldw + 2 * (size_t)(cp.tpb + tp0 + j)) = make_float4(f2x_lo(v.x), f2x_lo(v.y), f2x_hi(v.x), f2x_hi(v.y));
     }
 }
 
@@ -575,7 +635,7 @@ __host__ __device__ inline void body_colB_fwd(const Col2Params& cp, const cpd* _
 __host__ __device__ inline void body_colB_inv(const Col2Params& cp, cpd* __restrict__ v2, const float2* __restrict__ w, size_t ldw,
                                               const int* __restrict__ plane_ptr, const Col2Entry* __restrict__ ents, int plane,
                                               int tile, int tid, int nthr, cpd* smem) {
-    const int x2 = cp.x2, np = cp.np, hp = cp.ns / 2;
+    const int x2 = cp.x2, np = cp.np, hp = cp.vhp, tpn = cp.tpn;
     const int tp0 = tile * np;
     const cpd zero = dmake(vbc(0.f), vbc(0.f));
     for (int i = tid; i < np * cp.fstride; i += nthr) smem[i] = zero;
@@ -584,9 +644,9 @@ __host__ __device__ inline void body_colB_inv(const Col2Params& cp, cpd* __restr
     const int sh = cp.np_shift;
     for (int i = tid; i < (ne << sh); i += nthr) {
         const int ei = i >> sh, j = i & (np - 1);
-        if (tp0 + j >= hp) continue;
+        if (tp0 + j >= tpn) continue;
         const Col2Entry e = ents[e0 + ei];
-        const float4 u = *reinterpret_cast<const float4*>(w + (size_t)e.slot * ldw + 2 * (tp0 + j));
+        const float4 u = *reinterpret_cast<const float4*>(w + (size_t)e.slot * ldw + 2 * (size_t)(cp.tpb + tp0 + j));
         cpd v = dmake(f2x_set(u.x, u.z), f2x_set(u.y, u.w));
         if (e.flags & 1) v.y = vneg(v.y);
         smem[j * cp.fstride + e.pos] = v;
@@ -595,7 +655,7 @@ __host__ __device__ inline void body_colB_inv(const Col2Params& cp, cpd* __restr
     fft_inverse_stages_dual(smem, cp.plb, cp.twb, np, cp.fstride, tid, nthr);
     for (int i = tid; i < (x2 << sh); i += nthr) {
         const int c2 = i >> sh, j = i & (np - 1);
-        if (tp0 + j < hp) v2[((size_t)plane * x2 + c2) * hp + tp0 + j] = smem[j * cp.fstride + c2];
+        if (tp0 + j < tpn) v2[((size_t)plane * x2 + c2) * hp + tp0 + j] = smem[j * cp.fstride + c2];
     }
 }
 
@@ -605,19 +665,19 @@ __host__ __device__ inline void body_colB_inv(const Col2Params& cp, cpd* __restr
 // on contiguous groups) writes only the kept wavenumber rows straight to global memory; shared memory is
 // used once, for the transposition between the two stages.  need[plane][k2] = (slot of X[k1' + X1*k2] or -1,
 // slot whose value is conj(P[k2]): >= 0 both directions, <= -2 encodes -2-slot for the inverse only, -1 none).
-template <int RA, int RB>
+template <int RA, int RB, bool PIPE = false>
 __host__ __device__ inline void body_colB_fwd_fused(const Col2Params& cp, const cpd* __restrict__ v2, float2* __restrict__ w,
                                                     size_t ldw, const int2* __restrict__ need, int plane, int tile, int tid,
-                                                    int nthr, cpd* smem) {
-    const int x2 = cp.x2, np = cp.np, sh = cp.np_shift, hp = cp.ns / 2, fs = cp.fstride;
+                                                    int nthr, cpd* smem, int tpb, int tpn, L2Pol pol = L2Pol{0, 0}) {
+    const int x2 = cp.x2, np = cp.np, sh = cp.np_shift, hp = cp.vhp, fs = cp.fstride;
     const int tp0 = tile * np;
     const cpd zero = dmake(vbc(0.f), vbc(0.f));
     for (int it = tid; it < (RB << sh); it += nthr) {              // item = (n, j)
         const int n = it >> sh, j = it & (np - 1);
-        const bool ok = tp0 + j < hp;
+        const bool ok = tp0 + j < tpn;
         cpd v[RA];
         const cpd* src = v2 + ((size_t)plane * x2 + n) * hp + tp0 + j;
-        static_for<RA>([&](auto qc) { constexpr int q = decltype(qc)::value; v[q] = ok ? src[(size_t)(RB * q) * hp] : zero; });
+        static_for<RA>([&](auto qc) { constexpr int q = decltype(qc)::value; v[q] = ok ? ldc<PIPE>(src + (size_t)(RB * q) * hp, pol.keep) : zero; });
         DFTD<RA, false>::run(v);
         apply_stage_twiddles<RA, false, true>(v, cp.twb[n]);
         cpd* dst = smem + j * fs + n;
@@ -627,48 +687,43 @@ __host__ __device__ inline void body_colB_fwd_fused(const Col2Params& cp, const 
     const int2* nd = need + (size_t)plane * x2;
     for (int it = tid; it < (RA << sh); it += nthr) {              // item = (group m, j)
         const int m = it >> sh, j = it & (np - 1);
-        if (tp0 + j >= hp) continue;
+        if (tp0 + j >= tpn) continue;
         cpd v[RB];
         const cpd* src = smem + j * fs + RB * m;
         static_for<RB>([&](auto ic) { constexpr int i = decltype(ic)::value; v[i] = src[i]; });
         DFTD<RB, false>::run(v);
+        float2* wo = w + 2 * (size_t)(tpb + tp0 + j);
         static_for<RB>([&](auto ic) {
             constexpr int i = decltype(ic)::value;
             const int2 e = nd[m + RA * i];
             const cpd z = v[outpos<RB>(i)];
-            if (e.x >= 0)
-                *reinterpret_cast<float4*>(w + (size_t)e.x * ldw + 2 * (tp0 + j)) = make_float4(f2x_lo(z.x), f2x_lo(z.y), f2x_hi(z.x), f2x_hi(z.y));
-            if (e.y >= 0)
-                *reinterpret_cast<float4*>(w + (size_t)e.y * ldw + 2 * (tp0 + j)) = make_float4(f2x_lo(z.x), -f2x_lo(z.y), f2x_hi(z.x), -f2x_hi(z.y));
+            if (e.x >= 0) st16<PIPE>(wo + (size_t)e.x * ldw, make_float4(f2x_lo(z.x), f2x_lo(z.y), f2x_hi(z.x), f2x_hi(z.y)), pol.stream);
+            if (e.y >= 0) st16<PIPE>(wo + (size_t)e.y * ldw, make_float4(f2x_lo(z.x), -f2x_lo(z.y), f2x_hi(z.x), -f2x_hi(z.y)), pol.stream);
         });
     }
 }
 
-template <int RA, int RB>
+template <int RA, int RB, bool PIPE = false>
 __host__ __device__ inline void body_colB_inv_fused(const Col2Params& cp, cpd* __restrict__ v2, const float2* __restrict__ w,
                                                     size_t ldw, const int2* __restrict__ need, int plane, int tile, int tid,
-                                                    int nthr, cpd* smem) {
-    const int x2 = cp.x2, np = cp.np, sh = cp.np_shift, hp = cp.ns / 2, fs = cp.fstride;
+                                                    int nthr, cpd* smem, int tpb, int tpn, L2Pol pol = L2Pol{0, 0}) {
+    const int x2 = cp.x2, np = cp.np, sh = cp.np_shift, hp = cp.vhp, fs = cp.fstride;
     const int tp0 = tile * np;
-    const cpd zero = dmake(vbc(0.f), vbc(0.f));
     const int2* nd = need + (size_t)plane * x2;
     for (int it = tid; it < (RA << sh); it += nthr) {              // item = (group m, j): undo the radix-RB stage
         const int m = it >> sh, j = it & (np - 1);
-        const bool ok = tp0 + j < hp;
+        const bool ok = tp0 + j < tpn;
         cpd v[RB];
+        const float2* wi = w + 2 * (size_t)(tpb + tp0 + j);
         static_for<RB>([&](auto ic) {
             constexpr int i = decltype(ic)::value;
             const int2 e = nd[m + RA * i];
             const int sd = e.x, sm = (e.y >= 0) ? e.y : ((e.y <= -2) ? -2 - e.y : -1);
-            cpd z = zero;
-            if (ok && sd >= 0) {
-                const float4 u = *reinterpret_cast<const float4*>(w + (size_t)sd * ldw + 2 * (tp0 + j));
-                z = dmake(f2x_set(u.x, u.z), f2x_set(u.y, u.w));
-            } else if (ok && sm >= 0) {
-                const float4 u = *reinterpret_cast<const float4*>(w + (size_t)sm * ldw + 2 * (tp0 + j));
-                z = dmake(f2x_set(u.x, u.z), f2x_set(-u.y, -u.w));
-            }
-            v[i] = z;
+            const int sl = sd >= 0 ? sd : sm;                           // one predicated load, sign applied afterwards
+            const float sg = sd >= 0 ? 1.f : -1.f;
+            float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ok && sl >= 0) u = ld16<PIPE>(wi + (size_t)sl * ldw, pol.stream);
+            v[i] = dmake(f2x_set(u.x, u.z), f2x_set(sg * u.y, sg * u.w));
         });
         DFTD<RB, true>::run(v);
         cpd* dst = smem + j * fs + RB * m;
@@ -677,14 +732,14 @@ __host__ __device__ inline void body_colB_inv_fused(const Col2Params& cp, cpd* _
     D4W_SYNC();
     for (int it = tid; it < (RB << sh); it += nthr) {              // item = (n, j): undo the radix-RA stage
         const int n = it >> sh, j = it & (np - 1);
-        if (tp0 + j >= hp) continue;
+        if (tp0 + j >= tpn) continue;
         cpd v[RA];
         const cpd* src = smem + j * fs + n;
         static_for<RA>([&](auto mc) { constexpr int m = decltype(mc)::value; v[m] = src[RB * m]; });
         apply_stage_twiddles<RA, true, false>(v, cp.twb[n]);
         DFTD<RA, true>::run(v);
         cpd* dst = v2 + ((size_t)plane * x2 + n) * hp + tp0 + j;
-        static_for<RA>([&](auto qc) { constexpr int q = decltype(qc)::value; dst[(size_t)(RB * q) * hp] = v[outpos<RA>(q)]; });
+        static_for<RA>([&](auto qc) { constexpr int q = decltype(qc)::value; stc<PIPE>(dst + (size_t)(RB * q) * hp, v[outpos<RA>(q)], pol.keep); });
     }
 }
 
@@ -968,13 +1023,13 @@ template <int X1>
 static __global__ void __launch_bounds__(128)
 k_colA_fwd(Col2Params cp, const float* __restrict__ x, cpd* __restrict__ v2, const float* __restrict__ taper) {
     const int t4 = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t4 < cp.ns / 4) body_colA_fwd<X1>(cp, x, v2, taper, blockIdx.y, t4);
+    if (t4 < cp.tpn / 2) body_colA_fwd<X1>(cp, x, v2, taper, blockIdx.y, t4, cp.tpb);
 }
 template <int X1>
 static __global__ void __launch_bounds__(128)
 k_colA_inv(Col2Params cp, const cpd* __restrict__ v2, float* __restrict__ y) {
     const int t4 = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t4 < cp.ns / 4) body_colA_inv<X1>(cp, v2, y, blockIdx.y, t4);
+    if (t4 < cp.tpn / 2) body_colA_inv<X1>(cp, v2, y, blockIdx.y, t4, cp.tpb);
 }
 static __global__ void __launch_bounds__(160, 3)
 k_colB_fwd(Col2Params cp, const cpd* __restrict__ v2, float2* __restrict__ w, size_t ldw, const int* __restrict__ plane_ptr,
@@ -990,13 +1045,88 @@ k_colB_inv(Col2Params cp, cpd* __restrict__ v2, const float2* __restrict__ w, si
 template <int RA, int RB>
 static __global__ void __launch_bounds__(160, 3)
 k_colB_fwd_fused(Col2Params cp, const cpd* __restrict__ v2, float2* __restrict__ w, size_t ldw, const int2* __restrict__ need) {
-    body_colB_fwd_fused<RA, RB>(cp, v2, w, ldw, need, blockIdx.y, blockIdx.x, threadIdx.x, blockDim.x, reinterpret_cast<cpd*>(d4w_dyn_smem));
+    body_colB_fwd_fused<RA, RB>(cp, v2, w, ldw, need, blockIdx.y, blockIdx.x, threadIdx.x, blockDim.x, reinterpret_cast<cpd*>(d4w_dyn_smem), cp.tpb, cp.tpn);
 }
 template <int RA, int RB>
 static __global__ void __launch_bounds__(160, 3)
 k_colB_inv_fused(Col2Params cp, cpd* __restrict__ v2, const float2* __restrict__ w, size_t ldw, const int2* __restrict__ need) {
-    body_colB_inv_fused<RA, RB>(cp, v2, w, ldw, need, blockIdx.y, blockIdx.x, threadIdx.x, blockDim.x, reinterpret_cast<cpd*>(d4w_dyn_smem));
+    body_colB_inv_fused<RA, RB>(cp, v2, w, ldw, need, blockIdx.y, blockIdx.x, threadIdx.x, blockDim.x, reinterpret_cast<cpd*>(d4w_dyn_smem), cp.tpb, cp.tpn);
 }
+
+// ---- single-launch pipelined level A + level B ------------------------------------------------------------------
+// The record is cut into time chunks of cp.vhp sample pairs.  CTAs take tickets in start order; ticket -> (slot, role):
+// slot s holds the producer CTAs of chunk s followed by the consumer CTAs of chunk s - lag (forward: level A produces V,
+// level B consumes it; inverse: the other way round).  V lives in a ring of nbuf > lag chunk buffers that stays in L2:
+// a consumer waits until all producers of its chunk have signalled, a producer re-using a ring slot waits for the
+// consumers of the chunk that held it.  Every wait is on CTAs with smaller tickets, which have already started, so
+// the scheme cannot deadlock whatever the dispatch order.
+struct PipeParams {
+    int nchunks, lag, nbuf;
+    int nA, nB;                  // level-A / level-B CTAs per chunk
+    int cq, rpc;                 // level A: quads per row handled by one CTA, c2 rows per CTA (cq * rpc <= blockDim)
+    int tiles;                   // level B: np-pair tiles per chunk
+    int hints;                   // L2 eviction-priority hints on/off
+    unsigned* cnt;               // [0] ticket, [1 .. nchunks] A done, [1 + nchunks .. 2 nchunks] B done
+    size_t vbuf_elems;           // cpd elements per ring slot
+};
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void pipe_wait(const unsigned* p, unsigned target) {
+    if (threadIdx.x == 0) {
+        unsigned v;
+        for (;;) {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+            if (v >= target) break;
+            __nanosleep(64);
+        }
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ void pipe_signal(unsigned* p) {
+    __syncthreads();
+    if (threadIdx.x == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" :: "l"(p) : "memory");
+}
+
+template <int X1, int RA, int RB, bool INV>
+static __global__ void __launch_bounds__(160, 3)
+k_col2_pipe(Col2Params cp, PipeParams pp, const float* __restrict__ x, float* __restrict__ y, cpd* v2, float2* w, size_t ldw,
+            const int2* __restrict__ need, const float* __restrict__ taper) {
+    __shared__ unsigned s_ticket;
+    if (threadIdx.x == 0) s_ticket = atomicAdd(pp.cnt, 1u);
+    __syncthreads();
+    const int per = pp.nA + pp.nB;
+    const int slot = (int)(s_ticket / (unsigned)per), r = (int)(s_ticket % (unsigned)per);
+    const int nfirst = INV ? pp.nB : pp.nA;                 // producers come first in a slot
+    const bool first = r < nfirst;
+    const int c = first ? slot : slot - pp.lag;
+    if (c < 0 || c >= pp.nchunks) return;
+    const int idx = first ? r : r - nfirst;
+    const bool roleA = first != INV;
+    unsigned* cntA = pp.cnt + 1;
+    unsigned* cntB = pp.cnt + 1 + pp.nchunks;
+    const int tpb = c * cp.vhp, tpn = min(cp.vhp, cp.ns / 2 - tpb);
+    cpd* vb = v2 + (size_t)(c % pp.nbuf) * pp.vbuf_elems;
+    const L2Pol pol = make_l2pol(pp.hints != 0);
+    if (first) { if (c >= pp.nbuf) pipe_wait((INV ? cntA : cntB) + (c - pp.nbuf), (unsigned)(INV ? pp.nA : pp.nB)); }
+    else pipe_wait((INV ? cntB : cntA) + c, (unsigned)(INV ? pp.nB : pp.nA));
+    if (roleA) {
+        const int row = (int)threadIdx.x / pp.cq, q = (int)threadIdx.x - row * pp.cq;
+        const int c2 = idx * pp.rpc + row;
+        if (row < pp.rpc && c2 < cp.x2 && q < tpn / 2) {
+            if constexpr (!INV) body_colA_fwd<X1, true>(cp, x, vb, taper, c2, q, tpb, pol);
+            else body_colA_inv<X1, true>(cp, vb, y, c2, q, tpb, pol);
+        }
+        pipe_signal(cntA + c);
+    } else {
+        const int plane = idx / pp.tiles, tile = idx - plane * pp.tiles;
+        if (tile * cp.np < tpn) {
+            if constexpr (!INV) body_colB_fwd_fused<RA, RB, true>(cp, vb, w, ldw, need, plane, tile, threadIdx.x, blockDim.x, reinterpret_cast<cpd*>(d4w_dyn_smem), tpb, tpn, pol);
+            else body_colB_inv_fused<RA, RB, true>(cp, vb, w, ldw, need, plane, tile, threadIdx.x, blockDim.x, reinterpret_cast<cpd*>(d4w_dyn_smem), tpb, tpn, pol);
+        }
+        pipe_signal(cntB + c);
+    }
+}
+#endif
 
 static __global__ void k_mask_rowmax(MaskParams mp, unsigned int* rowmax, int fchunk) {
     const int k = blockIdx.y;

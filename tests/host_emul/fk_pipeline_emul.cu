@@ -21,9 +21,9 @@ template <int T1> static void split_all(bool inv, float2* w, size_t ldw, int t2,
 }
 template <int X1> static void colA_all(bool inv, const Col2Params& c2p, const float* x, cpd* v2, float* y, const float* taper) {
     for (int c2 = 0; c2 < c2p.x2; ++c2)
-        for (int t4 = 0; t4 < c2p.ns / 4; ++t4) {
-            if (inv) body_colA_inv<X1>(c2p, v2, y, c2, t4);
-            else body_colA_fwd<X1>(c2p, x, v2, taper, c2, t4);
+        for (int t4 = 0; t4 < c2p.tpn / 2; ++t4) {
+            if (inv) body_colA_inv<X1>(c2p, v2, y, c2, t4, c2p.tpb);
+            else body_colA_fwd<X1>(c2p, x, v2, taper, c2, t4, c2p.tpb);
         }
 }
 static void colA_dispatch(bool inv, const Col2Params& c2p, const float* x, cpd* v2, float* y, const float* taper) {
@@ -46,8 +46,8 @@ template <bool INV>
 static bool colB_fused_emul(const FkHostPlan& hp, const Col2Params& c2p, cpd* v2, float2* w, size_t ldw, const int2* need, int pl, int tb, cpd* smem) {
 #define EM_FUSED(RA, RB)                                                                                     \
     if (hp.fused_ra == RA && hp.fused_rb == RB) {                                                            \
-        if constexpr (!INV) body_colB_fwd_fused<RA, RB>(c2p, v2, w, ldw, need, pl, tb, 0, 1, smem);          \
-        else body_colB_inv_fused<RA, RB>(c2p, v2, w, ldw, need, pl, tb, 0, 1, smem);                         \
+        if constexpr (!INV) body_colB_fwd_fused<RA, RB>(c2p, v2, w, ldw, need, pl, tb, 0, 1, smem, c2p.tpb, c2p.tpn);          \
+        else body_colB_inv_fused<RA, RB>(c2p, v2, w, ldw, need, pl, tb, 0, 1, smem, c2p.tpb, c2p.tpn);                         \
         return true;                                                                                         \
     }
     EM_FUSED(16, 16) EM_FUSED(16, 20) EM_FUSED(16, 25) EM_FUSED(20, 16) EM_FUSED(20, 20) EM_FUSED(20, 25)
@@ -101,17 +101,21 @@ int main(int argc, char** argv) {
     if (two) {
         c2p.plb = hp.plb; c2p.twb = hp.tw_x2.data(); c2p.twn = hp.tw_col.data(); c2p.nx = nx; c2p.ns = ns; c2p.x1 = hp.x1; c2p.x2 = hp.x2;
         c2p.planes = hp.planes; c2p.np = hp.np2; c2p.fstride = hp.fstride2; c2p.np_shift = hp.np2 == 8 ? 3 : hp.np2 == 4 ? 2 : hp.np2 == 2 ? 1 : 0;
-        v2.resize((size_t)hp.planes * hp.x2 * (ns / 2));
+        c2p.vhp = hp.chunk_pairs; c2p.tpb = 0; c2p.tpn = hp.chunk_pairs;
+        v2.resize((size_t)hp.planes * hp.x2 * hp.chunk_pairs);
         std::vector<Col2EntryHost> eh; build_col2_entries(hp, k2slot, plane_ptr, eh);
         for (auto& e : eh) ents2.push_back(Col2Entry{e.pos, e.slot, e.flags, 0});
         smem.resize(std::max(smem.size(), hp.colb_smem / sizeof(float2) + 16));
         if (hp.fused_ra) build_col2_need(hp, k2slot, need2);
-        colA_dispatch(false, c2p, x.data(), v2.data(), nullptr, taper ? hp.taper.data() : nullptr);
-        const int ntb = (ns / 2 + hp.np2 - 1) / hp.np2;
-        for (int pl = 0; pl < hp.planes; ++pl)
-            for (int tb = 0; tb < ntb; ++tb)
-                if (!(hp.fused_ra && colB_fused_emul<false>(hp, c2p, v2.data(), w.data(), ldw, need2.data(), pl, tb, reinterpret_cast<cpd*>(smem.data()))))
-                    body_colB_fwd(c2p, v2.data(), w.data(), ldw, plane_ptr.data(), ents2.data(), pl, tb, 0, 1, reinterpret_cast<cpd*>(smem.data()));
+        for (int tpb = 0; tpb < ns / 2; tpb += hp.chunk_pairs) {
+            c2p.tpb = tpb; c2p.tpn = std::min(hp.chunk_pairs, ns / 2 - tpb);
+            colA_dispatch(false, c2p, x.data(), v2.data(), nullptr, taper ? hp.taper.data() : nullptr);
+            const int ntb = (c2p.tpn + hp.np2 - 1) / hp.np2;
+            for (int pl = 0; pl < hp.planes; ++pl)
+                for (int tb = 0; tb < ntb; ++tb)
+                    if (!(hp.fused_ra && colB_fused_emul<false>(hp, c2p, v2.data(), w.data(), ldw, need2.data(), pl, tb, reinterpret_cast<cpd*>(smem.data()))))
+                        body_colB_fwd(c2p, v2.data(), w.data(), ldw, plane_ptr.data(), ents2.data(), pl, tb, 0, 1, reinterpret_cast<cpd*>(smem.data()));
+        }
     }
     if (nact && !two)
         for (int b = 0; b < ntiles; ++b) {
@@ -128,14 +132,16 @@ int main(int argc, char** argv) {
             for (int k1 = 0; k1 < hp.t1; ++k1) body_row_mid(rp, w.data(), ldw, tab.data(), (size_t)ns, k1, s, 0, 1, smem.data());
     }
     if (hp.t1 > 1 && nact) split_dispatch(hp.t1, true, w.data(), ldw, hp.t2, hp.twT.data(), nact);
-    if (two) {
-        const int ntb = (ns / 2 + hp.np2 - 1) / hp.np2;
-        for (int pl = 0; pl < hp.planes; ++pl)
-            for (int tb = 0; tb < ntb; ++tb)
-                if (!(hp.fused_ra && colB_fused_emul<true>(hp, c2p, v2.data(), w.data(), ldw, need2.data(), pl, tb, reinterpret_cast<cpd*>(smem.data()))))
-                    body_colB_inv(c2p, v2.data(), w.data(), ldw, plane_ptr.data(), ents2.data(), pl, tb, 0, 1, reinterpret_cast<cpd*>(smem.data()));
-        colA_dispatch(true, c2p, nullptr, v2.data(), y.data(), nullptr);
-    }
+    if (two)
+        for (int tpb = 0; tpb < ns / 2; tpb += hp.chunk_pairs) {
+            c2p.tpb = tpb; c2p.tpn = std::min(hp.chunk_pairs, ns / 2 - tpb);
+            const int ntb = (c2p.tpn + hp.np2 - 1) / hp.np2;
+            for (int pl = 0; pl < hp.planes; ++pl)
+                for (int tb = 0; tb < ntb; ++tb)
+                    if (!(hp.fused_ra && colB_fused_emul<true>(hp, c2p, v2.data(), w.data(), ldw, need2.data(), pl, tb, reinterpret_cast<cpd*>(smem.data()))))
+                        body_colB_inv(c2p, v2.data(), w.data(), ldw, plane_ptr.data(), ents2.data(), pl, tb, 0, 1, reinterpret_cast<cpd*>(smem.data()));
+            colA_dispatch(true, c2p, nullptr, v2.data(), y.data(), nullptr);
+        }
     for (int b = 0; b < ntiles && !two; ++b) {
         if (hp.dual) body_col_inv_dual(cp, w.data(), ldw, slot_pos.data(), nact, y.data(), b, 0, 1, reinterpret_cast<cpd*>(smem.data()));
         else body_col_inv(cp, w.data(), ldw, slot_pos.data(), nact, y.data(), b, 0, 1, smem.data());

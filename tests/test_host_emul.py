@@ -62,6 +62,8 @@ CASES = [(40, 240, 1, False, None), (45, 175, 1, True, None), (38, 120, 2, False
          (10000, 16, 1, False, None),      # the bench column plan (two-level 25 x 400, fused 20 x 20 level B)
          (10000, 10, 1, True, {"D4W_COLB_RA": "16"}), (10000, 8, 1, False, {"D4W_COLB_RA": "25"}),
          (10000, 8, 1, False, {"D4W_COLB_FUSED": "0"}),      # shared-memory engine level B
+         (10000, 44, 1, True, {"D4W_COL_CHUNK_PAIRS": "8"}),  # three time chunks, the last one ragged
+         (6400, 36, 1, True, {"D4W_COL_X1": "16", "D4W_COL_CHUNK_PAIRS": "8", "D4W_COLB_FUSED": "0"}),
          (6400, 12, 1, False, {"D4W_COL_X1": "16"}), (8000, 8, 1, True, {"D4W_COL_X1": "20"}),
          (10000, 8, 1, False, {"D4W_COL_TWO_LEVEL": "0"}),   # single-level dual column kernels (20x20x25)
          (400, 24, 1, True, None), (320, 12, 1, True, {"D4W_COL_X1": "16"}), (500, 16, 1, False, {"D4W_COL_X1": "20"})]
