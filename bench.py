@@ -29,17 +29,21 @@ METRIC = "DAS channels/sec through f-k filter"
 CPU_SAMPLE_NX = 250                 # bounded CPU sample: 250 channels x the full 120 000 samples
 
 
-NCU_TRAFFIC_STEP = 21.1e9        # bytes per step, see traffic_source
-NCU_TRAFFIC_P5 = 6.44e9          # k_col_inv_tma, ncu dram bytes per launch
+# ncu --set full dram__bytes_read.sum + dram__bytes_write.sum per launch (profiles/r01d_fk_pipe.txt; P2/P4 at their
+# algorithmic 2.60 GB each)
+NCU_TRAFFIC = {3: {"step": 7.34e9 + 2.60e9 + 3.27e9 + 2.60e9 + 8.04e9, "p5": 8.04e9,
+                   "src": "profiles/r01d_fk_pipe.txt (P1 7.34 + P5 8.04 GB) + profiles/r01c_fk_tma_radix25.txt (P3 3.27 GB)"},
+               1: {"step": 21.1e9, "p5": 6.44e9, "src": "profiles/r01c_fk_tma_radix25.txt (P1 6.18 + P3 3.27 + P5 6.44 GB)"}}
+COL_KERNEL = {0: "k_col_inv_dual", 1: "k_col_inv_tma", 2: "k_colB_inv_fused + k_colA_inv", 3: "k_col2_pipe<inverse>"}
 
 
-def dominant(pass_ms, peak):
+def dominant(pass_ms, peak, scheme):
     """SURVEY 8(d) K3 (inverse pass back to real samples): 4 B read + 4 B written per (channel, sample)."""
     ms = pass_ms[4]
     alg = 8 * NX * NS
     ach = alg / (ms * 1e-3) / 1e9
-    return {"name": "k_col_inv_tma (P5, C2R over channels)", "ms": round(ms, 4), "algorithmic_bytes": alg,
-            "achieved": round(ach, 1), "frac": round(ach / peak, 4), "traffic": NCU_TRAFFIC_P5}
+    return {"name": COL_KERNEL.get(scheme, "?") + " (P5, C2R over channels)", "ms": round(ms, 4), "algorithmic_bytes": alg,
+            "achieved": round(ach, 1), "frac": round(ach / peak, 4), "traffic": NCU_TRAFFIC.get(scheme, {}).get("p5")}
 
 
 def measured_peak():
@@ -69,9 +73,12 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def count_since(self, t_begin):
+        return sum(1 for t, _ in self.rows if t >= t_begin)
+
+    def stop(self, t_begin=0.0, window="timed region"):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -81,7 +88,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for t, r in self.rows:
+            if t < t_begin:
+                continue
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
                 for n, v in zip(names, r[3:7]):
@@ -91,7 +100,7 @@ class ClockSampler:
                 pass
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def cpu_sample_inputs():
@@ -172,6 +181,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()                      # nvidia-smi needs ~1 s to come up: start it before the warm-up
     for _ in range(warmup):
         flt(x, out=y)
     # ---- per-pass device times (CUDA events on the launching stream) -------------------
@@ -191,19 +203,28 @@ def main():
             pass_ms[i] += ev[r][i].elapsed_time(ev[r][i + 1]) / reps
 
     # ---- the timed region: exactly K steps ------------------------------------------------
-    sampler = ClockSampler(local)
     n0 = L.d4w_launch_count()
     barrier()
-    if rank == 0:
-        sampler.start()
+    t_begin = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
         flt(x, out=y)
     e1.record()
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
     launches = L.d4w_launch_count() - n0
+    clocks = None
+    if rank == 0:
+        # nvidia-smi reports every 100 ms; a short timed region (K steps of ~8 ms) may see fewer than three reports, so
+        # the identical step keeps running, untimed, until three reports have been taken under the same load
+        window = "timed region"
+        t_cont = time.perf_counter()
+        while sampler.proc and sampler.count_since(t_begin) < 3 and time.perf_counter() - t_cont < 3.0:
+            for _ in range(8):
+                flt(x, out=y)
+            torch.cuda.synchronize()
+            window = "timed region + untimed continuation of the same step (region shorter than 3 nvidia-smi periods)"
+        clocks = sampler.stop(t_begin, window)
     ms = e0.elapsed_time(e1)
     if world > 1:
         t = torch.tensor([ms], device="cuda")
@@ -276,6 +297,7 @@ def main():
         algo_bytes = ALGO_BYTES_PER_SAMPLE * NX * NS
         achieved = algo_bytes / (ms_step * 1e-3) / 1e9
         traffic = flt.traffic_bytes()
+        scheme = flt.plan.col_scheme
         kernels = {n: {"ms": round(pass_ms[i], 4), "actual_bytes": traffic[n],
                        "actual_gbs": round(traffic[n] / (pass_ms[i] * 1e-3) / 1e9, 1) if pass_ms[i] > 0 else None}
                    for i, n in enumerate(names)}
@@ -286,13 +308,14 @@ def main():
                                        f"{FAN}), one matrix per GPU",
                            "l2": "inputs (4.8 GB) exceed the 126 MB L2; no flush needed",
                            "rows_kept": flt.rows_kept, "rows_total": NX // 2 + 1,
-                           "plan": {"t1": flt.plan.t1, "t2": flt.plan.t2, "col_tile_samples": flt.plan.tile}},
+                           "plan": {"t1": flt.plan.t1, "t2": flt.plan.t2, "col_tile_samples": flt.plan.tile,
+                                    "col_scheme": scheme}},
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                             "frac": round(achieved / peak, 4), "traffic": NCU_TRAFFIC_STEP,
-                             "traffic_source": "ncu --set full dram__bytes_read+write per launch, profiles/r01c_fk_tma_radix25.txt "
-                                               "(P1 6.18 + P3 3.27 + P5 6.44 GB) + P2/P4 at their algorithmic 2.60 GB each",
-                             "dominant_kernel": dominant(pass_ms, peak),
+                             "frac": round(achieved / peak, 4), "traffic": NCU_TRAFFIC.get(scheme, {}).get("step"),
+                             "traffic_source": "ncu --set full dram__bytes_read+write per launch, "
+                                               + NCU_TRAFFIC.get(scheme, {}).get("src", "n/a") + " + P2/P4 at their algorithmic 2.60 GB each",
+                             "dominant_kernel": dominant(pass_ms, peak, scheme),
                              "peak_source": peak_src,
                              "scope": "whole f-k filter = 5 kernels per step; achieved = 24 B/(channel*sample) algorithmic bytes "
                                       "(SURVEY 8d) / step time; actual_bytes per kernel below are lower because wavenumber rows "

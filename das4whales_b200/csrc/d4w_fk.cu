@@ -216,7 +216,8 @@ extern "C" int d4w_fk_debug_phases(d4w_fk_plan* pl, unsigned long long* host8) {
 extern "C" int d4w_fk_plan_info(const d4w_fk_plan* pl, int* info) {
     if (!pl || !info) return fail(D4W_ERR_ARG, "d4w_fk_plan_info: null argument");
     info[0] = pl->t1; info[1] = pl->t2; info[2] = 2 * pl->col.nc; info[3] = pl->col.pl.nstages;
-    info[4] = pl->row.pl.nstages; info[5] = pl->col_threads; info[6] = pl->row_threads; info[7] = 0;
+    info[4] = pl->row.pl.nstages; info[5] = pl->col_threads; info[6] = pl->row_threads;
+    info[7] = pl->pipe.nchunks ? 3 : pl->two_level ? 2 : pl->col.tma ? 1 : 0;
     return D4W_OK;
 }
 

@@ -35,6 +35,7 @@ class _Plan:
         info = _lib.ffi.new("int[8]")
         _lib.check(L.d4w_fk_plan_info(self.ptr, info), "fk plan info")
         self.t1, self.t2, self.tile, self.col_stages, self.row_stages = info[0], info[1], info[2], info[3], info[4]
+        self.col_scheme = int(info[7])
         self.workspace = None
 
     def get_workspace(self, nbytes):

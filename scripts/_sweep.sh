@@ -1,3 +1,5 @@
-for cfg in "D4W_PIPE_PF=0" "D4W_PIPE_PF=1" "D4W_PIPE_PF=2" "D4W_PIPE_PF=4" "D4W_COL_PIPE=0 D4W_COL_CHUNK_MB=0" "D4W_PIPE_PF=0"; do
-  echo "== $cfg"; env $cfg timeout 120 python scripts/gpu_tune_fk.py --one 2>&1 | tail -1
-done
+timeout 900 python -u -m pytest tests -m gpu -x -q --timeout 300 2>&1 | tail -4
+timeout 600 python bench.py > gpurun_out/r01e_bench_n1.json 2> gpurun_out/r01e_bench_n1.err; tail -c 600 gpurun_out/r01e_bench_n1.json
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_ -c 60 --csv --log-file gpurun_out/r01e_launches.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/r01e_launches.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_col2_pipe|k_row" -s 10 -c 5 -o gpurun_out/r01e_fk -f python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/r01e_fk.log 2>&1
+tail -2 gpurun_out/r01e_fk.log

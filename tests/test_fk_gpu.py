@@ -196,3 +196,38 @@ def test_tma_column_kernels_many_tiles_repeatable(dw, nx, ns):
     assert np.array_equal(y1, y2)
     ref = O.fk_filter_filt(x.astype(np.float64), O.fk_filter_design((nx, ns), sel, DX, FS))
     assert rel_err(y1, ref)[0] <= TOL
+
+
+COLUMN_SCHEMES = [{"D4W_COL_TWO_LEVEL": "0"},                                   # single-level persistent TMA kernels
+                  {"D4W_COL_TWO_LEVEL": "0", "D4W_COL_TMA": "0"},               # single-level cp.async dual kernels
+                  {"D4W_COL_PIPE": "0"},                                        # two-level, separate A / B launches
+                  {"D4W_COL_PIPE": "0", "D4W_COL_CHUNK_PAIRS": "64"},           # ... in time chunks
+                  {"D4W_COL_PIPE": "0", "D4W_COLB_FUSED": "0"},                 # shared-memory engine level B
+                  {"D4W_COLB_RA": "16"},                                        # pipelined, 16 x 25 level B
+                  {"D4W_PIPE_CQ": "40", "D4W_PIPE_LAG": "3"},                   # pipelined, narrower chunks / deeper ring
+                  {"D4W_PIPE_HINTS": "0"}]
+
+
+@pytest.mark.parametrize("env", COLUMN_SCHEMES)
+def test_column_schemes_agree(dw, monkeypatch, env):
+    """Every column-transform scheme (the default is the pipelined two-level one) gives the oracle's answer, is
+    repeatable bit for bit, and the ragged last chunk (ns/2 = 1100 pairs, chunks of 160) is handled."""
+    import torch
+    from das4whales_b200 import fk
+    nx, ns = 10000, 2200
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((nx, ns)).astype(np.float32)
+    sel = [0, nx, 1]
+    ref = O.fk_filter_filt(x.astype(np.float64), O.fk_filter_design((nx, ns), sel, DX, FS), tapering=True)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    fk.free_plans()
+    try:
+        mask = dw.dsp.fk_filter_design((nx, ns), sel, DX, FS)
+        xd = torch.from_numpy(x).cuda()
+        y1 = dw.dsp.fk_filter_filt(xd.clone(), mask, tapering=True).cpu().numpy()
+        y2 = dw.dsp.fk_filter_filt(xd.clone(), mask, tapering=True).cpu().numpy()
+    finally:
+        fk.free_plans()
+    assert np.array_equal(y1, y2)
+    assert rel_err(y1, ref)[0] <= TOL
