@@ -130,7 +130,7 @@ extern "C" int d4w_fk_plan_create(d4w_fk_plan** out, int nx, int ns, int device)
     pl->row_smem = hp.row_smem;
     pl->row_threads = env_int("D4W_ROW_THREADS", 256);
     const auto &twc = hp.tw_col, &twr = hp.tw_row, &twT = hp.twT;
-    const auto &p2k = hp.pos2k, &k2p = hp.k2pos, &p2kr = hp.pos2k_row;
+    const auto &p2k = hp.pos2k, &k2p = hp.k2pos, &p2kr = hp.pos2k_row_tab;
     const auto& tap = hp.taper;
     pl->h_k2pos = hp.k2pos;
     pl->hostplan = hp;
@@ -162,6 +162,7 @@ extern "C" int d4w_fk_plan_create(d4w_fk_plan** out, int nx, int ns, int device)
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_col_fwd<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_col_inv<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_row_mid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_row_mid_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_row_mid_dual, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
     if (e != cudaSuccess) {
         std::string msg = std::string("d4w_fk_plan_create: ") + cudaGetErrorString(e);
@@ -541,8 +542,12 @@ extern "C" int d4w_fk_apply_pass_ex(d4w_fk_plan* pl, d4w_fk_mask* m, const float
                 return D4W_OK;
             }
             dim3 grid(pl->t1, slot_count);
-            k_row_mid<<<grid, pl->row_threads, pl->row_smem, stream>>>(pl->row, w, ldw, m->d_table + (size_t)slot_begin * pl->ns,
-                                                                       (size_t)pl->ns);
+            if (pl->hostplan.row_fused)
+                k_row_mid_fused<<<grid, pl->row_threads, pl->row_smem, stream>>>(pl->row, w, ldw, m->d_table + (size_t)slot_begin * pl->ns,
+                                                                                 (size_t)pl->ns);
+            else
+                k_row_mid<<<grid, pl->row_threads, pl->row_smem, stream>>>(pl->row, w, ldw, m->d_table + (size_t)slot_begin * pl->ns,
+                                                                           (size_t)pl->ns);
             D4W_CHECK_LAUNCH("k_row_mid");
             return D4W_OK;
         }

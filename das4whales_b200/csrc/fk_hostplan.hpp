@@ -12,6 +12,7 @@ struct FkHostPlan {
     int t1 = 1, t2 = 0, nc = 1, nc_shift = 0, fstride = 0, aligned = 0;
     int dual = 0, npair = 0, npair_shift = 0, aligned16 = 0, tma = 0, col_max_radix = 0;
     int row_dual = 0;
+    int row_fused = 0;                // k_row_mid_fused: first stage from global memory, last stage + mask in registers
     // two-level column transform (nx = x1 * x2), see fk_kernels.cuh
     int two_level = 0, x1 = 0, x2 = 0, planes = 0, np2 = 0, fstride2 = 0;
     FftPlan plb{};
@@ -25,6 +26,7 @@ struct FkHostPlan {
     FftPlan colpl{}, rowpl{};
     std::vector<float2> tw_col, tw_row, twT;
     std::vector<int> pos2k, k2pos, pos2k_row;
+    std::vector<int> pos2k_row_tab;   // frequency of each entry of P3's mask table (table order depends on row_fused)
     std::vector<float> taper;
     size_t col_smem = 0, row_smem = 0;
 };
@@ -205,6 +207,17 @@ inline int build_fk_hostplan(int nx, int ns, size_t smem_cap, FkHostPlan& hp, st
     hp.k2pos.assign((size_t)nx, 0);
     for (int p = 0; p < nx; ++p) hp.k2pos[hp.pos2k[p]] = p;
     hp.pos2k_row = make_pos2freq(hp.rowpl);
+    hp.pos2k_row_tab = hp.pos2k_row;
+    {
+        const int nst = hp.rowpl.nstages;
+        auto inreg = [](int r) { for (int q : inreg_radices()) if (q == r) return true; return false; };
+        if (!hp.row_dual && env_int("D4W_ROW_FUSED", 1) && nst >= 2 && inreg(hp.rowpl.radix[0]) && inreg(hp.rowpl.radix[nst - 1])) {
+            hp.row_fused = 1;
+            const int rl = hp.rowpl.radix[nst - 1], G = hp.t2 / rl;
+            for (int m = 0; m < rl; ++m)
+                for (int j = 0; j < G; ++j) hp.pos2k_row_tab[(size_t)m * G + j] = hp.pos2k_row[(size_t)j * rl + m];
+        }
+    }
     hp.taper = tukey_window(ns, 0.03);
     return 0;
 }

@@ -743,6 +743,79 @@ __host__ __device__ inline void body_colB_inv_fused(const Col2Params& cp, cpd* _
     }
 }
 
+
+// ---- fused row kernel: first stage straight from global memory, last stage . mask . its inverse in registers ----
+// The T2-point piece makes one trip through shared memory per middle stage instead of one per stage plus a mask
+// pass.  Table order for this kernel: tab[m * (n / RL) + j] belongs to position j * RL + m of the engine's order.
+template <int R>
+__host__ __device__ inline void row_first_fwd(const float2* __restrict__ g, float2* __restrict__ s, const float2* __restrict__ tw,
+                                              int n_total, int tid, int nthr) {
+    const int L = n_total / R;
+    for (int n = tid; n < L; n += nthr) {
+        float2 v[R];
+        static_for<R>([&](auto qc) { constexpr int q = decltype(qc)::value; v[q] = g[n + q * L]; });
+        DFT<R, false>::run(v);
+        float2 p[R];
+        twiddle_powers<R>(tw[n], p);
+        static_for<R>([&](auto mc) { constexpr int m = decltype(mc)::value; s[n + m * L] = (m > 0) ? cmul(v[m], p[m]) : v[m]; });
+    }
+}
+template <int R>
+__host__ __device__ inline void row_first_inv(float2* __restrict__ g, const float2* __restrict__ s, const float2* __restrict__ tw,
+                                              int n_total, int tid, int nthr) {
+    const int L = n_total / R;
+    for (int n = tid; n < L; n += nthr) {
+        float2 v[R], p[R];
+        twiddle_powers<R>(tw[n], p);
+        static_for<R>([&](auto mc) { constexpr int m = decltype(mc)::value; const float2 u = s[n + m * L]; v[m] = (m > 0) ? cmulc(u, p[m]) : u; });
+        DFT<R, true>::run(v);
+        static_for<R>([&](auto qc) { constexpr int q = decltype(qc)::value; g[n + q * L] = v[q]; });
+    }
+}
+template <int R>
+__host__ __device__ inline void row_last_masked(float2* __restrict__ s, const float* __restrict__ tab, int n_total, int tid, int nthr) {
+    const int G = n_total / R;
+    for (int j = tid; j < G; j += nthr) {
+        float2* base = s + j * R;
+        float2 v[R];
+        static_for<R>([&](auto qc) { constexpr int q = decltype(qc)::value; v[q] = base[q]; });
+        DFT<R, false>::run(v);
+        static_for<R>([&](auto mc) { constexpr int m = decltype(mc)::value; const float c = tab[m * G + j]; v[m].x *= c; v[m].y *= c; });
+        DFT<R, true>::run(v);
+        static_for<R>([&](auto qc) { constexpr int q = decltype(qc)::value; base[q] = v[q]; });
+    }
+}
+#define D4W_ROW_RADIX_SWITCH(r, CALL)                                                                         \
+    switch (r) {                                                                                              \
+        case 2: { CALL(2) } break; case 3: { CALL(3) } break; case 4: { CALL(4) } break; case 5: { CALL(5) } break;         \
+        case 6: { CALL(6) } break; case 8: { CALL(8) } break; case 10: { CALL(10) } break; case 12: { CALL(12) } break;     \
+        case 15: { CALL(15) } break; case 16: { CALL(16) } break; case 20: { CALL(20) } break; default: { CALL(25) } break; \
+    }
+__host__ __device__ inline bool row_radix_inreg(int r) {
+    return r == 2 || r == 3 || r == 4 || r == 5 || r == 6 || r == 8 || r == 10 || r == 12 || r == 15 || r == 16 || r == 20 || r == 25;
+}
+__host__ __device__ inline void body_row_mid_fused(const RowParams& rp, float2* __restrict__ w, size_t ldw,
+                                                   const float* __restrict__ tab, size_t tab_slot_stride, int kt1, int slot,
+                                                   int tid, int nthr, float2* smem) {
+    const int n = rp.t2, nst = rp.pl.nstages;
+    float2* g = w + (size_t)slot * ldw + (size_t)kt1 * n;
+    const float* m = tab + (size_t)slot * tab_slot_stride + (size_t)kt1 * n;
+    const int r0 = rp.pl.radix[0], rl = rp.pl.radix[nst - 1];
+#define D4W_CALL(R) row_first_fwd<R>(g, smem, rp.tw, n, tid, nthr);
+    D4W_ROW_RADIX_SWITCH(r0, D4W_CALL)
+#undef D4W_CALL
+    D4W_SYNC();
+    fft_forward_stages(smem, rp.pl, rp.tw, 1, n, tid, nthr, 1, nst - 1);
+#define D4W_CALL(R) row_last_masked<R>(smem, m, n, tid, nthr);
+    D4W_ROW_RADIX_SWITCH(rl, D4W_CALL)
+#undef D4W_CALL
+    D4W_SYNC();
+    fft_inverse_stages(smem, rp.pl, rp.tw, 1, n, tid, nthr, 1, nst - 1);
+#define D4W_CALL(R) row_first_inv<R>(g, smem, rp.tw, n, tid, nthr);
+    D4W_ROW_RADIX_SWITCH(r0, D4W_CALL)
+#undef D4W_CALL
+}
+
 // ================================================================== __global__ wrappers
 #ifdef __CUDACC__
 extern __shared__ __align__(1024) float2 d4w_dyn_smem[];
@@ -1011,6 +1084,11 @@ k_row_split(float2* __restrict__ w, size_t ldw, int t2len, const float2* __restr
 static __global__ void __launch_bounds__(256, 2)
 k_row_mid(RowParams rp, float2* __restrict__ w, size_t ldw, const float* __restrict__ tab, size_t tab_slot_stride) {
     body_row_mid(rp, w, ldw, tab, tab_slot_stride, blockIdx.x, blockIdx.y, threadIdx.x, blockDim.x, d4w_dyn_smem);
+}
+
+static __global__ void __launch_bounds__(256, 2)
+k_row_mid_fused(RowParams rp, float2* __restrict__ w, size_t ldw, const float* __restrict__ tab, size_t tab_slot_stride) {
+    body_row_mid_fused(rp, w, ldw, tab, tab_slot_stride, blockIdx.x, blockIdx.y, threadIdx.x, blockDim.x, d4w_dyn_smem);
 }
 
 static __global__ void __launch_bounds__(128, 2)     // radix-25 dual butterflies need ~190 registers: 2 x 128-thread CTAs per SM

@@ -90,7 +90,7 @@ int main(int argc, char** argv) {
     for (int sl = 0; sl < nact; ++sl) slot_pos[sl] = make_int2(hp.k2pos[act[sl]], hp.k2pos[act[sl] == 0 ? 0 : nx - act[sl]]);
     std::vector<float> tab((size_t)std::max(nact, 1) * ns);
     const double scale = 1.0 / ((double)nx * ns);
-    for (size_t i = 0; i < (size_t)nact * ns; ++i) body_mask_build(mp, tab.data(), act.data(), hp.pos2k_row.data(), hp.t1, hp.t2, scale, i);
+    for (size_t i = 0; i < (size_t)nact * ns; ++i) body_mask_build(mp, tab.data(), act.data(), hp.pos2k_row_tab.data(), hp.t1, hp.t2, scale, i);
 
     std::vector<float2> w((size_t)std::max(nact, 1) * ns), smem((size_t)std::max(hp.col_smem, hp.row_smem) / sizeof(float2) + 16);
     std::vector<float> y((size_t)nx * ns, -777.f);
@@ -129,7 +129,10 @@ int main(int argc, char** argv) {
                 body_row_mid_dual(rp, w.data(), ldw, tab.data(), (size_t)ns, k1, pr, nact, 0, 1, reinterpret_cast<cpd*>(smem.data()));
     } else {
         for (int s = 0; s < nact; ++s)
-            for (int k1 = 0; k1 < hp.t1; ++k1) body_row_mid(rp, w.data(), ldw, tab.data(), (size_t)ns, k1, s, 0, 1, smem.data());
+            for (int k1 = 0; k1 < hp.t1; ++k1) {
+                if (hp.row_fused) body_row_mid_fused(rp, w.data(), ldw, tab.data(), (size_t)ns, k1, s, 0, 1, smem.data());
+                else body_row_mid(rp, w.data(), ldw, tab.data(), (size_t)ns, k1, s, 0, 1, smem.data());
+            }
     }
     if (hp.t1 > 1 && nact) split_dispatch(hp.t1, true, w.data(), ldw, hp.t2, hp.twT.data(), nact);
     if (two)
