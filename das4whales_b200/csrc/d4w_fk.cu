@@ -128,7 +128,7 @@ extern "C" int d4w_fk_plan_create(d4w_fk_plan** out, int nx, int ns, int device)
     pl->t1 = hp.t1; pl->t2 = hp.t2;
     pl->row.pl = hp.rowpl; pl->row.t1 = hp.t1; pl->row.t2 = hp.t2; pl->row.dual = hp.row_dual;
     pl->row_smem = hp.row_smem;
-    pl->row_threads = env_int("D4W_ROW_THREADS", 256);
+    pl->row_threads = std::min(256, std::max(32, env_int("D4W_ROW_THREADS", 256)));
     const auto &twc = hp.tw_col, &twr = hp.tw_row, &twT = hp.twT;
     const auto &p2k = hp.pos2k, &k2p = hp.k2pos, &p2kr = hp.pos2k_row_tab;
     const auto& tap = hp.taper;

@@ -1,7 +1,5 @@
-timeout 300 python -u -m pytest tests/test_fk_gpu.py -x -q --timeout 200 2>&1 | tail -3
-for cfg in "D4W_ROW_FUSED=1" "D4W_ROW_FUSED=0" "D4W_ROW_FUSED=1 D4W_ROW_THREADS=512" "D4W_ROW_FUSED=1 D4W_ROW_THREADS=192" "D4W_ROW_FUSED=1 D4W_ROW_THREADS=128"; do
-  echo "== $cfg"; env $cfg timeout 120 python scripts/gpu_tune_fk.py --one 2>&1 | tail -1
-done
-timeout 120 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
-timeout 200 python scripts/gpu_pcie_probe.py 2>&1 | tail -4
-timeout 300 python bench.py --no-cpu-baseline 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d['value'], d['ms_per_step'], d['clocks'], d['e2e']['ms_per_step'])"
+timeout 900 python -u -m pytest tests -m gpu -x -q --timeout 300 2>&1 | tail -3
+timeout 600 python bench.py > gpurun_out/r01f_bench_n1.json 2> gpurun_out/r01f_bench_n1.err; tail -c 300 gpurun_out/r01f_bench_n1.json
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_ -c 60 --csv --log-file gpurun_out/r01f_launches.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/r01f_launches.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_col2_pipe|k_row" -s 10 -c 5 -o gpurun_out/r01f_fk -f python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/r01f_fk.log 2>&1
+tail -1 gpurun_out/r01f_fk.log
