@@ -262,8 +262,21 @@ def main():
     e2e = None
     if not args.no_e2e:
         e2e_steps = min(steps, 6)
-        hx = torch.empty((NX, NS), dtype=torch.float32, pin_memory=True)
-        hy = [torch.empty((NX, NS), dtype=torch.float32, pin_memory=True) for _ in range(2)]
+        hx = hy = None
+        try:                                   # 3 x 4.8 GB of pinned host memory per rank
+            hx = torch.empty((NX, NS), dtype=torch.float32, pin_memory=True)
+            hy = [torch.empty((NX, NS), dtype=torch.float32, pin_memory=True) for _ in range(2)]
+            ok = 1
+        except Exception as exc:               # noqa: BLE001 -- report, never hang the other ranks
+            ok, why = 0, repr(exc)[:200]
+        if world > 1:
+            flag = torch.tensor([ok], device="cuda")
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            ok = int(flag.item())
+    if not args.no_e2e and not ok:
+        e2e = {"unavailable": "pinned host buffers could not be allocated on every rank"}
+        hx = hy = None
+    elif not args.no_e2e:
         hx.copy_(x)
         torch.cuda.synchronize()
         del y

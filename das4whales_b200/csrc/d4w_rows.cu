@@ -284,3 +284,43 @@ extern "C" int d4w_speccorr(const float* S, int nx, int nf, int nt, const float*
     D4W_CHECK_LAUNCH("k_speccorr");
     return D4W_OK;
 }
+
+// ---------------------------------------------------------------------------------- peak picking
+static void peak_level_sizes(int ns, int& nb1, int& nb2) { nb1 = (ns + kPkB - 1) / kPkB; nb2 = (nb1 + kPkB - 1) / kPkB; }
+
+extern "C" size_t d4w_find_peaks_workspace_bytes(int nx, int ns) {
+    if (nx < 1 || ns < 1) return 0;
+    int nb1, nb2; peak_level_sizes(ns, nb1, nb2);
+    return ((size_t)nx * (2 * (size_t)nb1 + 2 * (size_t)nb2 + 1)) * sizeof(float) + 256;
+}
+
+extern "C" int d4w_find_peaks(const float* x, int nx, int ns, double prominence, unsigned char* flags, void* ws, void* stream_v) {
+    if (!x || !flags || !ws || nx < 1 || ns < 1) return fail(D4W_ERR_ARG, "d4w_find_peaks: bad argument");
+    if (nx > 65535) return fail(D4W_ERR_UNSUPPORTED, "d4w_find_peaks: more than 65535 rows per call");
+    if (!(prominence >= 0.0)) return fail(D4W_ERR_ARG, "d4w_find_peaks: prominence must be >= 0");
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    D4W_CUDA_TRY(cudaMemsetAsync(flags, 0, (size_t)nx * ns, stream));
+    if (ns < 3) return D4W_OK;
+    int nb1, nb2; peak_level_sizes(ns, nb1, nb2);
+    float* bmax = reinterpret_cast<float*>(ws);
+    float* bmin = bmax + (size_t)nx * nb1;
+    float* smax = bmin + (size_t)nx * nb1;
+    float* smin = smax + (size_t)nx * nb2;
+    float* rowmin = smin + (size_t)nx * nb2;
+    k_peak_levels<<<nx, 256, 0, stream>>>(x, ns, bmax, bmin, smax, smin, rowmin, nb1, nb2);
+    D4W_CHECK_LAUNCH("k_peak_levels");
+    PeakLevels lv{bmax, bmin, smax, smin, nb1, nb2};
+    dim3 grid((ns + 255) / 256, nx);
+    k_peak_pick<<<grid, 256, 0, stream>>>(x, ns, lv, rowmin, prominence, flags);
+    D4W_CHECK_LAUNCH("k_peak_pick");
+    return D4W_OK;
+}
+
+// ---------------------------------------------------------------------------------- raw counts -> strain
+extern "C" int d4w_raw2strain(const void* raw, int raw_is_int32, int nx, int ns, double scale_factor, float* out, void* stream) {
+    if (!raw || !out || nx < 1 || ns < 1) return fail(D4W_ERR_ARG, "d4w_raw2strain: bad argument");
+    if (raw_is_int32) k_raw2strain<int><<<nx, 512, 0, (cudaStream_t)stream>>>(reinterpret_cast<const int*>(raw), out, ns, scale_factor);
+    else k_raw2strain<float><<<nx, 512, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float*>(raw), out, ns, scale_factor);
+    D4W_CHECK_LAUNCH("k_raw2strain");
+    return D4W_OK;
+}

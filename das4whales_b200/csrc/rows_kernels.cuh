@@ -7,6 +7,7 @@
 //   dsp.bp_filt (scipy filtfilt) and caller-side sosfiltfilt dsp.py:859-880, Example.py:55
 //   dsp.get_spectrogram / detect.get_sliced_nspectrogram     dsp.py:41-78, detect.py:334-408
 #pragma once
+#include <type_traits>
 #include "fft_smem.cuh"
 #include "fk_kernels.cuh"
 
@@ -457,6 +458,130 @@ k_row_max(const float* __restrict__ x, size_t n, float* __restrict__ mx) {
     if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = m;
     __syncthreads();
     if (threadIdx.x == 0) { for (int w = 1; w < 8; ++w) m = fmaxf(m, s[w]); mx[blockIdx.x] = fmaxf(m, s[0]); }
+}
+
+
+// ------------------------------------------------------------------ peak picking: find_peaks(x, prominence >= thr)
+// Semantics of scipy.signal.find_peaks as called by detect.pick_times_env / pick_times (detect.py:192, :271):
+//  * local maxima incl. flat tops: i is a plateau start if x[i-1] < x[i]; with e the first index > i whose value
+//    differs (at most n-1), it is a peak iff x[e] < x[i]; the reported index is (i + e - 1) / 2; never index 0 / n-1;
+//  * prominence = x[p] - max(left_min, right_min) where each side is the minimum over the run of samples <= x[p]
+//    adjacent to p (the run ends at the first strictly greater sample or the array end); compared in double.
+// The runs are walked hierarchically (64-sample blocks, 64-block superblocks with precomputed max / min), so a peak
+// costs O(64 * 3) reads in the worst case instead of O(n).
+constexpr int kPkB = 64;
+
+struct PeakLevels { const float *bmax, *bmin, *smax, *smin; int nb1, nb2; };
+
+static __global__ void __launch_bounds__(256)
+k_peak_levels(const float* __restrict__ x, int ns, float* bmax, float* bmin, float* smax, float* smin, float* rowmin, int nb1, int nb2) {
+    const size_t row = blockIdx.x;
+    const float* r = x + row * (size_t)ns;
+    float* bm = bmax + row * nb1; float* bn = bmin + row * nb1;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int b = wid; b < nb1; b += nw) {
+        const int i0 = b * kPkB + 2 * lane;
+        float mx = -INFINITY, mn = INFINITY;
+        if (i0 < ns) { const float v = r[i0]; mx = v; mn = v; }
+        if (i0 + 1 < ns) { const float v = r[i0 + 1]; mx = fmaxf(mx, v); mn = fminf(mn, v); }
+        for (int o = 16; o; o >>= 1) { mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o)); mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o)); }
+        if (lane == 0) { bm[b] = mx; bn[b] = mn; }
+    }
+    __syncthreads();
+    for (int sb = threadIdx.x; sb < nb2; sb += blockDim.x) {
+        float mx = -INFINITY, mn = INFINITY;
+        for (int b = sb * kPkB; b < min(nb1, (sb + 1) * kPkB); ++b) { mx = fmaxf(mx, bm[b]); mn = fminf(mn, bn[b]); }
+        smax[row * nb2 + sb] = mx; smin[row * nb2 + sb] = mn;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float mn = INFINITY;
+        for (int sb = 0; sb < nb2; ++sb) mn = fminf(mn, smin[row * nb2 + sb]);
+        rowmin[row] = mn;
+    }
+}
+
+// minimum over the run of samples <= v adjacent to position p on one side (DIR = -1 left, +1 right), v included
+template <int DIR>
+__device__ __forceinline__ float peak_side_min(const float* __restrict__ r, int ns, int p, float v, const float* __restrict__ bm,
+                                               const float* __restrict__ bn, const float* __restrict__ sm, const float* __restrict__ sn,
+                                               int nb1) {
+    float m = v;
+    int b = p / kPkB;
+    // rest of p's own block
+    if (DIR < 0) { for (int i = p - 1; i >= b * kPkB; --i) { const float u = r[i]; if (u > v) return m; m = fminf(m, u); } }
+    else { const int e = min(ns, (b + 1) * kPkB); for (int i = p + 1; i < e; ++i) { const float u = r[i]; if (u > v) return m; m = fminf(m, u); } }
+    b += DIR;
+    while (b >= 0 && b < nb1) {
+        const int sb = b / kPkB;
+        const bool sb_edge = DIR < 0 ? (b % kPkB == kPkB - 1) : (b % kPkB == 0);
+        const bool sb_full = DIR < 0 ? true : ((sb + 1) * kPkB <= nb1);
+        if (sb_edge && sb_full && !(sm[sb] > v)) { m = fminf(m, sn[sb]); b += DIR * kPkB; continue; }    // whole superblock <= v
+        if (!(bm[b] > v)) { m = fminf(m, bn[b]); b += DIR; continue; }                                   // whole block <= v
+        const int lo = b * kPkB, hi = min(ns, lo + kPkB);
+        if (DIR < 0) { for (int i = hi - 1; i >= lo; --i) { const float u = r[i]; if (u > v) return m; m = fminf(m, u); } }
+        else { for (int i = lo; i < hi; ++i) { const float u = r[i]; if (u > v) return m; m = fminf(m, u); } }
+        b += DIR;                                          // only reached when the block's maximum is a NaN artefact
+    }
+    return m;
+}
+
+static __global__ void __launch_bounds__(256)
+k_peak_pick(const float* __restrict__ x, int ns, PeakLevels lv, const float* __restrict__ rowmin, double thr, unsigned char* __restrict__ flags) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t row = blockIdx.y;
+    if (i < 1 || i >= ns - 1) return;
+    const float* r = x + row * (size_t)ns;
+    const float v = r[i];
+    if (!(r[i - 1] < v)) return;
+    int e = i + 1;
+    while (e < ns - 1 && r[e] == v) ++e;
+    if (!(r[e] < v)) return;
+    if ((double)v - (double)rowmin[row] < thr) return;                 // prominence <= height above the row minimum
+    const int p = (i + e - 1) / 2;
+    const float* bm = lv.bmax + row * lv.nb1; const float* bn = lv.bmin + row * lv.nb1;
+    const float* sm = lv.smax + row * lv.nb2; const float* sn = lv.smin + row * lv.nb2;
+    const float lmin = peak_side_min<-1>(r, ns, p, v, bm, bn, sm, sn, lv.nb1);
+    const float rmin = peak_side_min<+1>(r, ns, p, v, bm, bn, sm, sn, lv.nb1);
+    if ((double)v - (double)fmaxf(lmin, rmin) >= thr) flags[row * (size_t)ns + p] = 1;
+}
+
+// ------------------------------------------------------------------ loader-side fusion: raw counts -> strain
+// data_handle.raw2strain (data_handle.py:157-177): trace -= mean(trace, axis=1); trace *= scale_factor, here straight from
+// the on-disk int32 (or float32) counts to fp32 strain; one CTA per channel, mean accumulated in double.
+template <typename T>
+static __global__ void __launch_bounds__(512)
+k_raw2strain(const T* __restrict__ raw, float* __restrict__ out, int ns, double scale) {
+    const size_t row = blockIdx.x;
+    const T* r = raw + row * (size_t)ns;
+    float* o = out + row * (size_t)ns;
+    const bool vec = (ns % 4 == 0) && (((size_t)r | (size_t)o) % 16 == 0);
+    using V4 = typename std::conditional<std::is_same<T, int>::value, int4, float4>::type;
+    double acc = 0.0;
+    if (vec) {
+        const V4* r4 = reinterpret_cast<const V4*>(r);
+        for (int i = threadIdx.x; i < ns / 4; i += blockDim.x) { const V4 v = r4[i]; acc += ((double)v.x + (double)v.y) + ((double)v.z + (double)v.w); }
+    } else {
+        for (int i = threadIdx.x; i < ns; i += blockDim.x) acc += (double)r[i];
+    }
+    __shared__ double s_part[16];
+    for (int o2 = 16; o2; o2 >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o2);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    double mean = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) mean += s_part[w];
+    mean /= (double)ns;
+    if (vec) {                                               // second read of the row comes from L2
+        const V4* r4 = reinterpret_cast<const V4*>(r);
+        float4* o4 = reinterpret_cast<float4*>(o);
+        for (int i = threadIdx.x; i < ns / 4; i += blockDim.x) {
+            const V4 v = r4[i];
+            o4[i] = make_float4((float)(((double)v.x - mean) * scale), (float)(((double)v.y - mean) * scale),
+                                (float)(((double)v.z - mean) * scale), (float)(((double)v.w - mean) * scale));
+        }
+    } else {
+        for (int i = threadIdx.x; i < ns; i += blockDim.x) o[i] = (float)(((double)r[i] - mean) * scale);
+    }
 }
 
 }  // namespace d4w

@@ -68,17 +68,14 @@ def envelope(corr_m):
 
 def pick_times_env(corr_m, threshold):
     """Peaks of the Hilbert envelope with prominence >= threshold (reference: detect.py:169-195).
-    Envelope on the GPU; prominence search (branchy, ragged output) on the host -- SURVEY 8(f)."""
-    env = envelope(corr_m)
-    if _is_tensor(env):
-        env = env.cpu().numpy()
-    return [sp.find_peaks(e, prominence=threshold)[0] for e in env]
+    Envelope and scipy.signal.find_peaks' prominence search both run on the GPU (d4w_hilbert, d4w_find_peaks);
+    only the picks are copied back: list with one int64 index array per channel, like the reference."""
+    return _rows.find_peaks(_rows.envelope(_to_device(corr_m)), float(threshold))
 
 
 def pick_times(corr_m, threshold):
-    """Peaks of the raw correlogram (reference: detect.py:249-274)."""
-    c = corr_m.cpu().numpy() if _is_tensor(corr_m) else np.asarray(corr_m)
-    return [sp.find_peaks(r, prominence=threshold)[0] for r in c]
+    """Peaks of the raw correlogram with prominence >= threshold (reference: detect.py:249-274)."""
+    return _rows.find_peaks(_to_device(corr_m), float(threshold))
 
 
 pick_times_par = pick_times_env
@@ -86,8 +83,9 @@ pick_times_par = pick_times_env
 
 def convert_pick_times(peaks_indexes_m):
     """list of per-channel index arrays -> array([[channel...],[time...]]) (detect.py:277-303)."""
-    ch = [i for i, p in enumerate(peaks_indexes_m) for _ in p]
-    tt = [e for p in peaks_indexes_m for e in p]
+    counts = [len(p) for p in peaks_indexes_m]
+    ch = np.repeat(np.arange(len(counts), dtype=np.int64), counts)
+    tt = np.concatenate([np.asarray(p, dtype=np.int64) for p in peaks_indexes_m]) if counts else np.empty(0, dtype=np.int64)
     return np.asarray((ch, tt))
 
 

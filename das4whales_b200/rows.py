@@ -261,3 +261,47 @@ def spectro_correlate(S, kernel, median=None):
         _lib.check(_lib.lib().d4w_speccorr(_lib.ptr(S, "float*"), nx, nf, nt, _lib.ptr(K, "float*"), kw, _lib.ptr(median, "float*"),
                                            _lib.ptr(out, "float*"), _lib.stream_ptr()), "speccorr")
     return out
+
+
+def find_peaks_flags(x2d, prominence):
+    """scipy.signal.find_peaks(row, prominence=prominence) on every row of a [rows, n] float32 CUDA tensor;
+    returns a uint8 [rows, n] tensor with 1 at every accepted peak (reference call sites: detect.py:192, :271)."""
+    torch = _torch()
+    rows_, n = x2d.shape
+    L = _lib.lib()
+    flags = torch.empty((rows_, n), dtype=torch.uint8, device=x2d.device)
+    with torch.cuda.device(x2d.device.index):
+        ws = torch.empty(int(L.d4w_find_peaks_workspace_bytes(min(rows_, 65535), n)), dtype=torch.uint8, device=x2d.device)
+        for r0 in range(0, rows_, 65535):
+            r1 = min(rows_, r0 + 65535)
+            _lib.check(L.d4w_find_peaks(_lib.ptr(x2d[r0:r1], "float*"), r1 - r0, n, float(prominence),
+                                        _lib.ffi.cast("unsigned char*", flags[r0:r1].data_ptr()), _lib.ptr(ws, "void*"),
+                                        _lib.stream_ptr()), "find_peaks")
+    return flags
+
+
+def find_peaks(x2d, prominence):
+    """Per-row peak indices (list of int64 ndarrays, ascending) -- only the picks leave the GPU."""
+    import numpy as np
+    torch = _torch()
+    flags = find_peaks_flags(x2d, prominence)
+    nz = torch.nonzero(flags)                     # row-major order: rows ascending, indices ascending within a row
+    rows_ = x2d.shape[0]
+    if nz.numel() == 0:
+        return [np.empty(0, dtype=np.int64) for _ in range(rows_)]
+    nz = nz.cpu().numpy()
+    counts = np.bincount(nz[:, 0], minlength=rows_)
+    return np.split(nz[:, 1].astype(np.int64, copy=False), np.cumsum(counts)[:-1])
+
+
+def raw2strain(raw2d, scale_factor):
+    """(raw - mean_row) * scale_factor from int32 / float32 counts to float32 strain (data_handle.py:157-177)."""
+    torch = _torch()
+    if raw2d.dtype not in (torch.int32, torch.float32):
+        raise ValueError("raw2strain: raw data must be int32 or float32")
+    rows_, n = raw2d.shape
+    out = torch.empty((rows_, n), dtype=torch.float32, device=raw2d.device)
+    with torch.cuda.device(raw2d.device.index):
+        _lib.check(_lib.lib().d4w_raw2strain(_lib.ffi.cast("void*", raw2d.data_ptr()), 1 if raw2d.dtype == torch.int32 else 0,
+                                             rows_, n, float(scale_factor), _lib.ptr(out, "float*"), _lib.stream_ptr()), "raw2strain")
+    return out

@@ -160,6 +160,18 @@ int d4w_row_median(const float* dev_x, int nrows, size_t n, float* dev_median, v
 int d4w_row_max(const float* dev_x, int nrows, size_t n, float* dev_max, void* stream);
 int d4w_speccorr(const float* dev_S, int nx, int nf, int nt, const float* dev_K, int kw, const float* dev_median,
                  float* dev_out, void* stream);
+
+/* ---- peak picking -- detect.pick_times_env (detect.py:169-195, the find_peaks call :192) and detect.pick_times
+ *      (:249-274, :271): scipy.signal.find_peaks(row, prominence=threshold) on every row of a [nx][ns] float32 matrix
+ *      (flat tops -> plateau midpoint, prominence walked to the nearest strictly greater sample, compared in double).
+ *      flags[nx][ns] (bytes) is cleared and set to 1 at every accepted peak; ws needs
+ *      d4w_find_peaks_workspace_bytes(nx, ns) bytes. */
+size_t d4w_find_peaks_workspace_bytes(int nx, int ns);
+int d4w_find_peaks(const float* dev_x, int nx, int ns, double prominence, unsigned char* dev_flags, void* dev_ws, void* stream);
+
+/* ---- loader-side fusion -- data_handle.raw2strain (data_handle.py:157-177): out = (raw - mean_row(raw)) * scale_factor,
+ *      from the on-disk int32 counts (raw_is_int32 = 1) or float32 to fp32 strain; mean in double. */
+int d4w_raw2strain(const void* dev_raw, int raw_is_int32, int nx, int ns, double scale_factor, float* dev_out, void* stream);
 /* D4W_CDEF_END */
 
 #ifdef __cplusplus

@@ -183,6 +183,25 @@ def main():
     sc.update(ff=ff, tt=tt, ker=ker, S=S, xc2d=r)
     np.savez_compressed(os.path.join(OUT, "spectrocorr.npz"), **sc)
 
+    # ---- peak picking on the raw correlogram + ties / flat tops (a14) and raw2strain (8(f) rank 2) -----------
+    pkf = {}
+    rng = np.random.default_rng(11)
+    xq = np.round(rng.standard_normal((8, 700)) * 3.0) / 3.0            # quantised: many exact ties and plateaus
+    xq[3] = 0.25; xq[4] = np.arange(700) / 700.0; xq[5, 100:140] = 5.0
+    for thr in (0.0, 0.4, 2.0):
+        pk = detect.pick_times(xq, thr)
+        assert all(np.array_equal(a, b) for a, b in zip(pk, D.pick_times(xq, thr)))
+        pkf[f"picks_thr{thr}"] = detect.convert_pick_times(pk)
+    pkf["x"] = xq
+    np.savez_compressed(os.path.join(OUT, "picks.npz"), **pkf)
+    from oracle import data_oracle as DH
+    dh = ref_loader.load_data_handle()
+    raw = rng.integers(-2 ** 20, 2 ** 20, size=(12, 500)).astype(np.int32)
+    meta = {"scale_factor": 4.0838e-11 * 1550.0 / 2.0419}
+    ref_strain = dh.raw2strain(raw.astype(np.float64), meta)              # the reference works in place on float arrays
+    rep["raw2strain"] = close(ref_strain, DH.raw2strain(raw, meta), what="raw2strain")
+    np.savez_compressed(os.path.join(OUT, "raw2strain.npz"), raw=raw, scale_factor=meta["scale_factor"], strain=ref_strain)
+
     for k, v in rep.items():
         print(f"{k:24s} oracle-vs-reference rel err {v:.2e}")
     tot = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))

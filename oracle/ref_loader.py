@@ -76,3 +76,26 @@ def load():
     detect = _load("detect")
     _cache["mods"] = (dsp, detect)
     return dsp, detect
+
+
+def load_data_handle():
+    """The reference's data_handle module (unmodified) with its file-format dependencies stubbed out; only the
+    arithmetic helper raw2strain (data_handle.py:157-177) is used from it."""
+    if "dh" in _cache:
+        return _cache["dh"]
+    load()
+    for n in ("h5py", "wget", "nptdms", "dask", "dask.array", "xarray", "pyproj", "pandas"):
+        try:
+            importlib.import_module(n)
+        except Exception:
+            _stub(n)
+    if not hasattr(sys.modules["nptdms"], "TdmsFile"):
+        sys.modules["nptdms"].TdmsFile = type("TdmsFile", (), {})
+    if "dask" in sys.modules and not hasattr(sys.modules["dask"], "array") and "dask.array" in sys.modules:
+        sys.modules["dask"].array = sys.modules["dask.array"]
+    spec = importlib.util.spec_from_file_location("das4whales.data_handle", os.path.join(_SRC, "data_handle.py"))
+    m = importlib.util.module_from_spec(spec)
+    sys.modules[spec.name] = m
+    spec.loader.exec_module(m)
+    _cache["dh"] = m
+    return m

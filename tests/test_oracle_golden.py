@@ -123,3 +123,15 @@ def test_oracle_against_live_reference():
     assert rel_err(O.bp_filt(x, FS, 14, 30), dsp.bp_filt(x, FS, 14, 30))[0] <= 1e-13
     tpl = detect.gen_template_fincall(np.arange(ns) / FS, FS, 17.8, 28.8, 0.68)
     assert rel_err(D.compute_cross_correlogram(x, tpl), detect.compute_cross_correlogram(x, tpl))[0] <= 1e-13
+
+
+def test_picks_and_raw2strain_match_golden(golden):
+    """find_peaks(prominence) picks on rows full of ties / flat tops, and the loader's raw2strain."""
+    from oracle import data_oracle as DH
+    g = golden("picks")
+    for thr in (0.0, 0.4, 2.0):
+        got = D.convert_pick_times(D.pick_times(g["x"], thr))
+        assert np.array_equal(got, g[f"picks_thr{thr}"])
+    r = golden("raw2strain")
+    out = DH.raw2strain(r["raw"], {"scale_factor": float(r["scale_factor"])})
+    assert rel_err(out, r["strain"])[0] <= 1e-15

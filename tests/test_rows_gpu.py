@@ -186,3 +186,65 @@ def test_sosfiltfilt_chunked_equals_sequential(dw):
         import scipy.signal as sps
         ref = sps.sosfiltfilt(sos, x.cpu().numpy().astype(np.float64), axis=1)
         assert rel_err(y, ref)[0] <= 2e-5, spec
+
+
+def _scipy_picks(x32, thr):
+    import scipy.signal as sps
+    return [sps.find_peaks(np.asarray(r, dtype=np.float64), prominence=thr)[0] for r in x32]
+
+
+def test_find_peaks_golden_ties_and_plateaus(dw, golden):
+    """Device find_peaks(prominence) == the reference's picks, index for index, on rows built to have exact ties,
+    flat tops, a constant row, a monotone row and a long plateau (values are exactly representable in float32)."""
+    g = golden("picks")
+    x = g["x"]
+    for thr in (0.0, 0.4, 2.0):
+        got = dw.detect.pick_times(x, thr)
+        ref = _scipy_picks(x.astype(np.float32), thr)
+        assert len(got) == x.shape[0]
+        for a, b in zip(got, ref):
+            assert a.dtype == np.int64 and np.array_equal(a, b)
+        if thr != 2.0:     # multiples of 1/3: a prominence of exactly 2.0 is rounding-marginal in float64 and in float32
+            assert np.array_equal(dw.detect.convert_pick_times(got), g[f"picks_thr{thr}"])
+
+
+@pytest.mark.parametrize("ns", [2, 3, 64, 65, 4097, 120000])
+def test_find_peaks_vs_scipy_random(dw, ns):
+    """Bit-exact index parity with scipy.signal.find_peaks on the same float32 rows: white noise (many shallow peaks),
+    a smooth envelope-like row (few, wide peaks -> long prominence walks over blocks and superblocks), quantised rows."""
+    import torch
+    rng = np.random.default_rng(ns)
+    rows = [rng.standard_normal(ns), np.abs(np.sin(np.arange(ns) * 0.003)) * (1 + 0.1 * rng.standard_normal(ns)),
+            np.round(rng.standard_normal(ns) * 2) / 2, np.full(ns, 1.5), np.arange(ns, dtype=np.float64),
+            np.concatenate([np.zeros(ns // 2), np.ones(ns - ns // 2)])]
+    x = np.stack(rows).astype(np.float32)
+    xd = torch.from_numpy(x).cuda()
+    for thr in (0.0, 0.3, 1.0, 5.0):
+        got = dw.rows.find_peaks(xd, thr)
+        ref = _scipy_picks(x, thr)
+        for r, (a, b) in enumerate(zip(got, ref)):
+            assert np.array_equal(a, b), (ns, thr, r, len(a), len(b))
+
+
+def test_pick_times_env_pipeline_vs_oracle(dw, golden):
+    """Envelope (fp32 on the device) + device picking against the float64 reference picks: identical away from
+    threshold-marginal peaks; at least 99 % of the reference picks must be reproduced exactly."""
+    g = golden("matched_filter")
+    for tag in ("hf", "lf"):
+        got = dw.detect.convert_pick_times(dw.detect.pick_times_env(g["corr_" + tag], 0.05))
+        ref = g["picks_" + tag]
+        gs, rs = set(map(tuple, got.T.tolist())), set(map(tuple, ref.T.tolist()))
+        assert len(gs & rs) >= 0.99 * len(rs) and len(gs) <= 1.01 * len(rs) + 1
+
+
+def test_raw2strain_golden(dw, golden):
+    import torch
+    r = golden("raw2strain")
+    meta = {"scale_factor": float(r["scale_factor"])}
+    out = dw.data_handle.raw2strain(r["raw"], meta)                       # int32 ndarray -> float64 ndarray
+    assert out.dtype == np.float64 and rel_err(out, r["strain"])[0] <= 1e-6
+    outd = dw.data_handle.raw2strain(torch.from_numpy(r["raw"]).cuda(), meta)
+    assert outd.dtype == torch.float32 and rel_err(outd.cpu().numpy(), r["strain"])[0] <= 1e-6
+    f = r["raw"].astype(np.float64)
+    ret = dw.data_handle.raw2strain(f, meta)
+    assert ret is f and rel_err(f, r["strain"])[0] <= 1e-6                # in place for float arrays, like the reference
