@@ -173,6 +173,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-mf", action="store_true", help="skip the f-k + matched-filter (BASELINE configs[2]) leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -253,6 +254,35 @@ def main():
         ms = float(t.item())
     ms_step = ms / steps
     value = NX * world / (ms_step * 1e-3)
+
+    # ---- BASELINE configs[2]: f-k filter + fin-whale matched filter (HF + LF templates, one pass over the filtered data)
+    mf = None
+    if not args.no_mf:
+        import numpy as np
+        tgrid = np.arange(NS) / FS
+        tpls = [dw.detect.gen_template_fincall(tgrid, FS, 17.8, 28.8, 0.68), dw.detect.gen_template_fincall(tgrid, FS, 14.7, 21.8, 0.78)]
+        def fk_mf():
+            flt(x, out=y)
+            return dw.detect.compute_cross_correlograms(y, tpls)
+        outs = fk_mf(); del outs
+        barrier()
+        m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        mf_steps = min(steps, 5)
+        m0.record()
+        for _ in range(mf_steps):
+            outs = fk_mf(); del outs
+        m1.record()
+        barrier()
+        mf_ms = m0.elapsed_time(m1) / mf_steps
+        if world > 1:
+            t = torch.tensor([mf_ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            mf_ms = float(t.item())
+        mf = {"workload": "BASELINE configs[2]: the same matrix through the f-k filter, then detect.compute_cross_correlograms "
+                          "with the HF (17.8-28.8 Hz, 0.68 s) and LF (14.7-21.8 Hz, 0.78 s) fin-whale templates",
+              "value": NX * world / (mf_ms * 1e-3), "unit": "channels/s", "ms_per_step": mf_ms, "steps": mf_steps,
+              "algorithmic_bytes": (24 + 12) * NX * NS, "achieved_gbs": round((24 + 12) * NX * NS / (mf_ms * 1e-3) / 1e9, 1)}
+        torch.cuda.empty_cache()
 
     # ---- end to end through the public API with HOST buffers ---------------------------------
     # A stream of files: every step copies that step's strain matrix from pinned host memory, filters it
@@ -358,6 +388,8 @@ def main():
                 "clocks": clocks}
         if e2e:
             line["e2e"] = e2e
+        if mf:
+            line["fk_plus_matched_filter"] = mf
         if not args.no_cpu_baseline and world == 1:
             cv, ct = time_cpu_reference(steps=1, warmup=0)
             line["cpu_baseline"] = {"value": cv, "unit": "channels/s", "cores": 1, "kind": "port",

@@ -14,6 +14,8 @@ struct d4w_fft_plan {
     size_t smem_cap = 0;
     FftPlan pl{};
     std::vector<int> pos2k;
+    std::vector<int> tab2k;      // frequency of each entry of a multiplier table in d4w_xcorr's order
+    int fused = 0;               // k_xcorr_fused usable: >= 2 stages, first and last stage in-register radices
     float2* d_tw = nullptr;
     int* d_k2pos = nullptr;
 };
@@ -28,8 +30,24 @@ extern "C" int d4w_fft_plan_create(d4w_fft_plan** out, int n, int device) {
     auto p = new d4w_fft_plan();
     p->n = n; p->device = device; p->smem_cap = prop.sharedMemPerBlockOptin;
     std::string err;
-    if (!make_plan(n, env_int("D4W_BLOCK_MAX_RADIX", 25), p->pl, err, 128, 16)) { delete p; return fail(D4W_ERR_UNSUPPORTED, err); }
+    // overlap-save block lengths (rows.py _pick_block): big even radix first, small odd radix last suits k_xcorr_fused
+    const char* forced = std::getenv("D4W_BLOCK_PLAN");
+    const char* pref = n == 1250 ? "10,25,5" : n == 2500 ? "20,25,5" : n == 5000 ? "20,10,25" : n == 10000 ? "20,20,25" : nullptr;
+    bool have = false;
+    if (forced && *forced) have = make_plan_from_string(n, forced, p->pl);
+    if (!have && pref && env_int("D4W_XCORR_FUSED", 1)) have = make_plan_from_string(n, pref, p->pl);
+    if (!have && !make_plan(n, env_int("D4W_BLOCK_MAX_RADIX", 25), p->pl, err, 128, 16)) { delete p; return fail(D4W_ERR_UNSUPPORTED, err); }
     p->pos2k = make_pos2freq(p->pl);
+    p->tab2k = p->pos2k;
+    {
+        const int nst = p->pl.nstages;
+        if (env_int("D4W_XCORR_FUSED", 1) && nst >= 2 && row_radix_inreg(p->pl.radix[0]) && row_radix_inreg(p->pl.radix[nst - 1])) {
+            p->fused = 1;
+            const int rl = p->pl.radix[nst - 1], G = n / rl;
+            for (int m = 0; m < rl; ++m)
+                for (int j = 0; j < G; ++j) p->tab2k[(size_t)m * G + j] = p->pos2k[(size_t)j * rl + m];
+        }
+    }
     std::vector<int> k2pos((size_t)n);
     for (int i = 0; i < n; ++i) k2pos[p->pos2k[i]] = i;
     cudaError_t e = upload(&p->d_tw, make_twiddles(n));
@@ -50,6 +68,12 @@ extern "C" int d4w_fft_plan_destroy(d4w_fft_plan* p) {
 extern "C" int d4w_fft_plan_order(const d4w_fft_plan* p, int* host_pos2freq) {
     if (!p || !host_pos2freq) return fail(D4W_ERR_ARG, "d4w_fft_plan_order: null argument");
     std::memcpy(host_pos2freq, p->pos2k.data(), (size_t)p->n * sizeof(int));
+    return D4W_OK;
+}
+
+extern "C" int d4w_fft_plan_table_order(const d4w_fft_plan* p, int* host_tab2freq) {
+    if (!p || !host_tab2freq) return fail(D4W_ERR_ARG, "d4w_fft_plan_table_order: null argument");
+    std::memcpy(host_tab2freq, p->tab2k.data(), (size_t)p->n * sizeof(int));
     return D4W_OK;
 }
 
@@ -92,10 +116,16 @@ extern "C" int d4w_xcorr(d4w_fft_plan* p, const float* x, int nx, int ns, int va
     xp.nseg = (ns + valid - 1) / valid;
     const size_t smem = (size_t)3 * p->n * sizeof(float2);
     if (smem + 1024 > p->smem_cap) return fail(D4W_ERR_UNSUPPORTED, "d4w_xcorr: block length too large for shared memory");
-    D4W_CUDA_TRY(cudaFuncSetAttribute(k_xcorr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_cap - 1024));  // minus its static smem
     dim3 grid((xp.nseg + 1) / 2, nx);
-    k_xcorr<<<grid, 128, smem, (cudaStream_t)stream>>>(xp, x, (const float2*)dev_tabs, dev_stats, dev_segpre, dev_mu_over_m, out,
-                                                      (size_t)nx * ns);
+    if (p->fused) {
+        D4W_CUDA_TRY(cudaFuncSetAttribute(k_xcorr_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_cap - 1024));
+        k_xcorr_fused<<<grid, 128, smem, (cudaStream_t)stream>>>(xp, x, (const float2*)dev_tabs, dev_stats, dev_segpre, dev_mu_over_m, out,
+                                                                (size_t)nx * ns);
+    } else {
+        D4W_CUDA_TRY(cudaFuncSetAttribute(k_xcorr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_cap - 1024));  // minus its static smem
+        k_xcorr<<<grid, 128, smem, (cudaStream_t)stream>>>(xp, x, (const float2*)dev_tabs, dev_stats, dev_segpre, dev_mu_over_m, out,
+                                                          (size_t)nx * ns);
+    }
     D4W_CHECK_LAUNCH("k_xcorr");
     return D4W_OK;
 }
@@ -107,6 +137,7 @@ struct d4w_row_plan {
     float2 *d_tw = nullptr, *d_twT = nullptr;
     float* d_hilbert = nullptr;
     size_t row_smem = 0;
+    int fused = 0;               // split rows: middle pass by k_row_mid_fused (weights stored in its table order)
 };
 
 extern "C" int d4w_row_plan_create(d4w_row_plan** out, int ns, int device) {
@@ -123,9 +154,11 @@ extern "C" int d4w_row_plan_create(d4w_row_plan** out, int ns, int device) {
     p->row.pl = hp.rowpl; p->row.t1 = hp.t1; p->row.t2 = hp.t2;
     // analytic-signal weights of scipy.signal.hilbert (N = ns, no padding), scaled by 1/ns, transform order
     std::vector<float> h((size_t)ns);
+    p->fused = (hp.t1 > 1 && hp.row_fused) ? 1 : 0;
+    const std::vector<int>& order = p->fused ? hp.pos2k_row_tab : hp.pos2k_row;
     for (int kt1 = 0; kt1 < hp.t1; ++kt1)
         for (int pos = 0; pos < hp.t2; ++pos) {
-            const int f = kt1 + hp.t1 * hp.pos2k_row[pos];
+            const int f = kt1 + hp.t1 * order[pos];
             double wgt;
             if (ns % 2 == 0) wgt = (f == 0 || f == ns / 2) ? 1.0 : (f < ns / 2 ? 2.0 : 0.0);
             else wgt = (f == 0) ? 1.0 : (f <= (ns - 1) / 2 ? 2.0 : 0.0);
@@ -135,6 +168,7 @@ extern "C" int d4w_row_plan_create(d4w_row_plan** out, int ns, int device) {
     if (e == cudaSuccess) e = upload(&p->d_twT, hp.twT);
     if (e == cudaSuccess) e = upload(&p->d_hilbert, h);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_row_mid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_row_mid_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_hilbert_row, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin);
     if (e != cudaSuccess) { d4w_row_plan_destroy(p); return fail(D4W_ERR_CUDA, std::string("row plan: ") + cudaGetErrorString(e)); }
     p->row.tw = p->d_tw; p->row.twT = p->d_twT;
@@ -179,7 +213,8 @@ extern "C" int d4w_hilbert(d4w_row_plan* p, const float* x, float* out, int nx, 
     }
     D4W_CHECK_LAUNCH("k_hsplit_fwd");
     dim3 gmid(p->t1, nx);
-    k_row_mid<<<gmid, 256, p->row_smem, stream>>>(p->row, w, (size_t)p->ns, p->d_hilbert, (size_t)0);
+    if (p->fused) k_row_mid_fused<<<gmid, 256, p->row_smem, stream>>>(p->row, w, (size_t)p->ns, p->d_hilbert, (size_t)0);
+    else k_row_mid<<<gmid, 256, p->row_smem, stream>>>(p->row, w, (size_t)p->ns, p->d_hilbert, (size_t)0);
     D4W_CHECK_LAUNCH("k_row_mid");
     switch (p->t1) {
 #define D4W_HC(T) case T: k_hsplit_inv<T><<<grid, threads, 0, stream>>>(w, p->ns, out, p->t2, p->d_twT, mode, dev_stats); break;

@@ -167,6 +167,111 @@ k_xcorr(XcorrParams xp, const float* __restrict__ x, const float2* __restrict__ 
     }
 }
 
+// ---- fused variant (plans with >= 2 stages whose first and last stage are in-register radices) -------------------
+// Passes over shared memory per block: load + prefix, forward stages 0 .. n-2, then per template ONE pass doing the last
+// forward stage, the multiply with the template spectrum and the first inverse stage in registers (S is left intact for
+// the next template), the middle inverse stages, and the last inverse stage straight to global memory with the mu term.
+// Table order: tabs[t][m * (nb / RL) + j] belongs to engine position j * RL + m (d4w_fft_plan_table_order).
+template <int R>
+__device__ __forceinline__ void xcorr_last_fused(const float2* __restrict__ S, float2* __restrict__ B, const float2* __restrict__ tab,
+                                                 int nb, int tid, int nthr) {
+    const int G = nb / R;
+    for (int j = tid; j < G; j += nthr) {
+        float2 v[R];
+        static_for<R>([&](auto qc) { constexpr int q = decltype(qc)::value; v[q] = S[j * R + q]; });
+        DFT<R, false>::run(v);
+        static_for<R>([&](auto mc) { constexpr int m = decltype(mc)::value; v[m] = cmul(v[m], tab[m * G + j]); });
+        DFT<R, true>::run(v);
+        static_for<R>([&](auto qc) { constexpr int q = decltype(qc)::value; B[j * R + q] = v[q]; });
+    }
+}
+template <int R>
+__device__ __forceinline__ void xcorr_first_inv_out(const float2* __restrict__ B, const float2* __restrict__ P, const float2* __restrict__ tw,
+                                                    int nb, int V, int ta, int tb, int ns, float mu, bool use_p, float* __restrict__ o,
+                                                    int tid, int nthr) {
+    const int L = nb / R;
+    for (int n = tid; n < L; n += nthr) {
+        float2 v[R], p[R];
+        twiddle_powers<R>(tw[n], p);
+        static_for<R>([&](auto mc) { constexpr int m = decltype(mc)::value; const float2 u = B[n + m * L]; v[m] = (m > 0) ? cmulc(u, p[m]) : u; });
+        DFT<R, true>::run(v);
+        static_for<R>([&](auto qc) {
+            constexpr int q = decltype(qc)::value;
+            const int i = n + q * L;
+            if (i < V) {
+                float2 pr = make_float2(0.f, 0.f);
+                if (use_p) pr = P[i];
+                if (ta + i < ns) o[ta + i] = v[q].x + mu * pr.x;
+                if (tb + i < ns) o[tb + i] = v[q].y + mu * pr.y;
+            }
+        });
+    }
+}
+
+static __global__ void __launch_bounds__(128, 4)
+k_xcorr_fused(XcorrParams xp, const float* __restrict__ x, const float2* __restrict__ tabs, const double* __restrict__ stats,
+              const double* __restrict__ segpre, const double* __restrict__ mu_over_m, float* __restrict__ out, size_t out_tpl_stride) {
+    extern __shared__ float2 sm[];
+    float2* S = sm;
+    float2* B = sm + xp.nb;
+    float2* P = sm + 2 * xp.nb;
+    __shared__ float2 s_wsum[32];
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, wid = tid >> 5;
+    const int row = blockIdx.y;
+    const int seg_a = 2 * blockIdx.x, seg_b = seg_a + 1;
+    const int ns = xp.ns, nb = xp.nb, V = xp.valid, nst = xp.pl.nstages;
+    const int ta = seg_a * V, tb = seg_b * V;
+    const float* r = x + (size_t)row * ns;
+    float mean = 0.f, inv = 1.f;
+    if (xp.normalize) { mean = (float)stats[4 * (size_t)row]; inv = (float)(1.0 / stats[4 * (size_t)row + 1]); }
+    for (int i = tid; i < nb; i += nthr) {
+        const int ia = ta + i, ib = tb + i;
+        const float a = (ia < ns) ? (r[ia] - mean) * inv : 0.f;
+        const float b = (ib < ns) ? (r[ib] - mean) * inv : 0.f;
+        S[i] = make_float2(a, b);
+    }
+    __syncthreads();
+    if (xp.normalize) {
+        const int chunk = (V + nthr - 1) / nthr;
+        const int i0 = min(V, tid * chunk), i1 = min(V, i0 + chunk);
+        float2 loc = make_float2(0.f, 0.f);
+        for (int i = i0; i < i1; ++i) { loc.x += S[i].x; loc.y += S[i].y; }
+        float2 inc = loc;
+        for (int o = 1; o < 32; o <<= 1) {
+            const float ux = __shfl_up_sync(0xffffffffu, inc.x, o), uy = __shfl_up_sync(0xffffffffu, inc.y, o);
+            if (lane >= o) { inc.x += ux; inc.y += uy; }
+        }
+        if (lane == 31) s_wsum[wid] = inc;
+        __syncthreads();
+        float2 base = make_float2(0.f, 0.f);
+        for (int w = 0; w < wid; ++w) { base.x += s_wsum[w].x; base.y += s_wsum[w].y; }
+        float2 run = make_float2(base.x + inc.x - loc.x, base.y + inc.y - loc.y);
+        const float pa = (seg_a < xp.nseg) ? (float)segpre[(size_t)row * xp.nseg + seg_a] : 0.f;
+        const float pb = (seg_b < xp.nseg) ? (float)segpre[(size_t)row * xp.nseg + seg_b] : 0.f;
+        for (int i = i0; i < i1; ++i) {
+            P[i] = make_float2(pa + run.x, pb + run.y);
+            run.x += S[i].x; run.y += S[i].y;
+        }
+        __syncthreads();
+    }
+    fft_forward_stages(S, xp.pl, xp.tw, 1, nb, tid, nthr, 0, nst - 1);
+    const int r0 = xp.pl.radix[0], rl = xp.pl.radix[nst - 1];
+    for (int t = 0; t < xp.ntpl; ++t) {
+        const float2* tab = tabs + (size_t)t * nb;
+#define D4W_CALL(R) xcorr_last_fused<R>(S, B, tab, nb, tid, nthr);
+        D4W_ROW_RADIX_SWITCH(rl, D4W_CALL)
+#undef D4W_CALL
+        __syncthreads();
+        fft_inverse_stages(B, xp.pl, xp.tw, 1, nb, tid, nthr, 1, nst - 1);
+        const float mu = xp.normalize ? (float)mu_over_m[t] : 0.f;
+        float* o = out + (size_t)t * out_tpl_stride + (size_t)row * ns;
+#define D4W_CALL(R) xcorr_first_inv_out<R>(B, P, xp.tw, nb, V, ta, tb, ns, mu, xp.normalize != 0, o, tid, nthr);
+        D4W_ROW_RADIX_SWITCH(r0, D4W_CALL)
+#undef D4W_CALL
+        __syncthreads();
+    }
+}
+
 // ------------------------------------------------------------------ Hilbert envelope / SNR on the T1 x T2 row engine
 enum { EPI_ENV = 0, EPI_SNR = 1 };
 

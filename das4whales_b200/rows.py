@@ -34,6 +34,9 @@ class _FftPlan:
         order = np.empty(n, dtype=np.int32)
         _lib.check(L.d4w_fft_plan_order(self.ptr, _lib.ffi.cast("int*", order.ctypes.data)), "fft order")
         self.pos2freq = order
+        tab = np.empty(n, dtype=np.int32)
+        _lib.check(L.d4w_fft_plan_table_order(self.ptr, _lib.ffi.cast("int*", tab.ctypes.data)), "fft table order")
+        self.tab2freq = tab                      # order of the multiplier tables d4w_xcorr reads
 
 
 def fft_plan(n, device):
@@ -117,7 +120,7 @@ def cross_correlogram(x, templates, normalize=True):
     tabs = np.empty((len(taps), nb), dtype=np.complex64)
     for i, (c, m) in enumerate(zip(taps, ms)):
         spec = np.fft.fft(c, nb)
-        tabs[i] = (np.conj(spec) / (nb * m))[plan.pos2freq]
+        tabs[i] = (np.conj(spec) / (nb * m))[plan.tab2freq]
     out = torch.empty((len(taps), nx, ns), dtype=torch.float32, device=x.device)
     with torch.cuda.device(dev):
         tabs_d = torch.from_numpy(tabs.view(np.float32).reshape(len(taps), nb, 2)).to(x.device)

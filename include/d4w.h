@@ -110,6 +110,9 @@ int d4w_fft_plan_create(d4w_fft_plan** out, int n, int device);
 int d4w_fft_plan_destroy(d4w_fft_plan* plan);
 /* host_pos2freq[p] = DFT bin stored at position p after the forward transform (n ints) */
 int d4w_fft_plan_order(const d4w_fft_plan* plan, int* host_pos2freq);
+/* frequency index of each entry of the multiplier tables d4w_xcorr expects (the plan's transform order, regrouped
+ * so that the fused last stage reads them coalesced) */
+int d4w_fft_plan_table_order(const d4w_fft_plan* plan, int* host_tab2freq);
 
 /* ---- row statistics: np.mean / np.max(np.abs) / np.std(axis=1) used by
  *      detect.compute_cross_correlogram (detect.py:157) and dsp.snr_tr_array (dsp.py:975-976).
