@@ -136,6 +136,7 @@ struct d4w_row_plan {
     RowParams row{};
     float2 *d_tw = nullptr, *d_twT = nullptr;
     float* d_hilbert = nullptr;
+    float* d_sgn = nullptr;      // sgn(f)/ns in k_row_mid_fused's table order (two-rows-per-transform route)
     size_t row_smem = 0;
     int fused = 0;               // split rows: middle pass by k_row_mid_fused (weights stored in its table order)
 };
@@ -164,9 +165,15 @@ extern "C" int d4w_row_plan_create(d4w_row_plan** out, int ns, int device) {
             else wgt = (f == 0) ? 1.0 : (f <= (ns - 1) / 2 ? 2.0 : 0.0);
             h[(size_t)kt1 * hp.t2 + pos] = (float)(wgt / ns);
         }
+    std::vector<float> sg;
+    if (p->fused && env_int("D4W_HILBERT_PAIR", 1)) {
+        sg.resize((size_t)ns);
+        for (size_t i = 0; i < sg.size(); ++i) sg[i] = h[i] - (float)(1.0 / ns);      // h - 1: 0 at DC / Nyquist, +-1 elsewhere
+    }
     cudaError_t e = upload(&p->d_tw, hp.tw_row);
     if (e == cudaSuccess) e = upload(&p->d_twT, hp.twT);
     if (e == cudaSuccess) e = upload(&p->d_hilbert, h);
+    if (e == cudaSuccess && !sg.empty()) e = upload(&p->d_sgn, sg);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_row_mid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_row_mid_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_hilbert_row, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin);
@@ -179,14 +186,15 @@ extern "C" int d4w_row_plan_create(d4w_row_plan** out, int ns, int device) {
 extern "C" int d4w_row_plan_destroy(d4w_row_plan* p) {
     if (!p) return D4W_OK;
     DeviceGuard guard(p->device);
-    cudaFree(p->d_tw); cudaFree(p->d_twT); cudaFree(p->d_hilbert);
+    cudaFree(p->d_tw); cudaFree(p->d_twT); cudaFree(p->d_hilbert); cudaFree(p->d_sgn);
     delete p;
     return D4W_OK;
 }
 
 extern "C" size_t d4w_row_workspace_bytes(const d4w_row_plan* p, int nx) {
     if (!p || p->t1 == 1) return 16;
-    return (size_t)nx * p->ns * sizeof(float2);
+    const size_t rows = p->d_sgn ? (size_t)(nx + 1) / 2 : (size_t)nx;      // two real rows share one complex workspace row
+    return rows * p->ns * sizeof(float2);
 }
 
 extern "C" int d4w_hilbert(d4w_row_plan* p, const float* x, float* out, int nx, void* workspace, int mode,
@@ -202,6 +210,29 @@ extern "C" int d4w_hilbert(d4w_row_plan* p, const float* x, float* out, int nx, 
         return D4W_OK;
     }
     if (!workspace) return fail(D4W_ERR_ARG, "d4w_hilbert: workspace required for split rows");
+    if (p->d_sgn) {                                              // two real rows per complex transform
+        float2* w2 = (float2*)workspace;
+        const int npair = (nx + 1) / 2, thr = 128;
+        dim3 g2((p->t2 + thr - 1) / thr, npair);
+        switch (p->t1) {
+#define D4W_HC(T) case T: k_hsplit_fwd2<T><<<g2, thr, 0, stream>>>(x, nx, p->ns, w2, p->t2, p->d_twT); break;
+            D4W_HC(2) D4W_HC(3) D4W_HC(4) D4W_HC(5) D4W_HC(6) D4W_HC(8) D4W_HC(10) D4W_HC(12) D4W_HC(15) D4W_HC(16) D4W_HC(20) D4W_HC(25)
+#undef D4W_HC
+            default: return fail(D4W_ERR_UNSUPPORTED, "row split radix not built");
+        }
+        D4W_CHECK_LAUNCH("k_hsplit_fwd2");
+        dim3 gm(p->t1, npair);
+        k_row_mid_fused<<<gm, 256, p->row_smem, stream>>>(p->row, w2, (size_t)p->ns, p->d_sgn, (size_t)0);
+        D4W_CHECK_LAUNCH("k_row_mid_fused");
+        switch (p->t1) {
+#define D4W_HC(T) case T: k_hsplit_inv2<T><<<g2, thr, 0, stream>>>(w2, x, nx, p->ns, out, p->t2, p->d_twT, mode, dev_stats); break;
+            D4W_HC(2) D4W_HC(3) D4W_HC(4) D4W_HC(5) D4W_HC(6) D4W_HC(8) D4W_HC(10) D4W_HC(12) D4W_HC(15) D4W_HC(16) D4W_HC(20) D4W_HC(25)
+#undef D4W_HC
+            default: return fail(D4W_ERR_UNSUPPORTED, "row split radix not built");
+        }
+        D4W_CHECK_LAUNCH("k_hsplit_inv2");
+        return D4W_OK;
+    }
     float2* w = (float2*)workspace;
     const int threads = 128;
     dim3 grid((p->t2 + threads - 1) / threads, nx);

@@ -320,6 +320,66 @@ k_hsplit_inv(const float2* __restrict__ w, int ns, float* __restrict__ out, int 
     static_for<T1>([&](auto jc) { constexpr int j = decltype(jc)::value; dst[(size_t)j * t2len] = hilbert_epilogue(v[j], mode, var); });
 }
 
+// ---- two real rows per complex transform --------------------------------------------------------------------
+// The Hilbert transform is linear and maps real rows to real rows, so for z = a + i b one complex FFT -> (-i sgn f) -> IFFT
+// yields H(a) + i H(b): half the transforms and half the workspace traffic of the analytic-signal route.  The middle
+// pass multiplies by the real table sgn(f)/ns (0 at DC and Nyquist, scipy.signal.hilbert's h - 1); the factor -i is
+// applied here: with u = IFFT(Z sgn), H(a) = Im u and H(b) = -Re u; |hilbert(a)| = sqrt(a^2 + H(a)^2).
+__device__ __forceinline__ float hilbert_epilogue2(float x, float h, int mode, float var) {
+    const float p = x * x + h * h;
+    return mode == EPI_ENV ? sqrtf(p) : 10.0f * log10f(p / var);
+}
+template <int T1>
+static __global__ void __launch_bounds__(128)
+k_hsplit_fwd2(const float* __restrict__ x, int nx, int ns, float2* __restrict__ w, int t2len, const float2* __restrict__ twT) {
+    const int t2 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t2 >= t2len) return;
+    const size_t pr = blockIdx.y;
+    const float* sa = x + (2 * pr) * (size_t)ns + t2;
+    const bool has_b = 2 * pr + 1 < (size_t)nx;
+    const float* sb = sa + ns;
+    float2 v[T1];
+    static_for<T1>([&](auto jc) {
+        constexpr int j = decltype(jc)::value;
+        v[j] = make_float2(sa[(size_t)j * t2len], has_b ? sb[(size_t)j * t2len] : 0.f);
+    });
+    float2 p[T1];
+    twiddle_powers<T1>(twT[t2], p);
+    DFT<T1, false>::run(v);
+    float2* dst = w + pr * ns + t2;
+    static_for<T1>([&](auto jc) {
+        constexpr int j = decltype(jc)::value;
+        dst[(size_t)j * t2len] = (j > 0) ? cmul(v[j], p[j]) : v[j];
+    });
+}
+template <int T1>
+static __global__ void __launch_bounds__(128)
+k_hsplit_inv2(const float2* __restrict__ w, const float* __restrict__ x, int nx, int ns, float* __restrict__ out, int t2len,
+              const float2* __restrict__ twT, int mode, const double* __restrict__ stats) {
+    const int t2 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t2 >= t2len) return;
+    const size_t pr = blockIdx.y;
+    const float2* src = w + pr * ns + t2;
+    float2 v[T1];
+    static_for<T1>([&](auto jc) { constexpr int j = decltype(jc)::value; v[j] = src[(size_t)j * t2len]; });
+    float2 p[T1];
+    twiddle_powers<T1>(twT[t2], p);
+    static_for<T1>([&](auto jc) { constexpr int j = decltype(jc)::value; if constexpr (j > 0) v[j] = cmulc(v[j], p[j]); });
+    DFT<T1, true>::run(v);
+    const size_t ra = 2 * pr, rb = 2 * pr + 1;
+    const bool has_b = rb < (size_t)nx;
+    const float va = (mode == EPI_SNR) ? (float)stats[4 * ra + 2] : 1.f;
+    const float vb = (mode == EPI_SNR && has_b) ? (float)stats[4 * rb + 2] : 1.f;
+    const float* xa = x + ra * ns + t2;
+    float* oa = out + ra * ns + t2;
+    static_for<T1>([&](auto jc) {
+        constexpr int j = decltype(jc)::value;
+        const size_t o = (size_t)j * t2len;
+        oa[o] = hilbert_epilogue2(xa[o], v[j].y, mode, va);
+        if (has_b) oa[ns + o] = hilbert_epilogue2(xa[ns + o], v[j].x, mode, vb);
+    });
+}
+
 // whole row in one CTA (T1 == 1): real in -> FFT -> weights -> IFFT -> epilogue out
 static __global__ void __launch_bounds__(256, 2)
 k_hilbert_row(RowParams rp, const float* __restrict__ x, float* __restrict__ out, const float* __restrict__ tab, int mode,

@@ -126,7 +126,7 @@ int d4w_snr(const float* dev_x, float* dev_out, int nx, int ns, const double* de
 /* ---- matched filter: detect.compute_cross_correlogram / shift_xcorr (detect.py:96-166) as
  *      overlap-save FFT correlation; `plan` = fft plan of the block length nb, `valid` = nb - L + 1
  *      lags kept per block.  dev_tabs: ntpl x nb complex64 = conj(FFT_nb(template_t)) / (nb * m_t) in
- *      the plan's transform order.  With dev_stats != NULL rows are demeaned / peak-normalised and
+ *      the plan's table order (d4w_fft_plan_table_order).  With dev_stats != NULL rows are demeaned / peak-normalised and
  *      the mean-of-padded-template term mu_t/m_t * prefix is added (dev_mu_over_m: double[ntpl]).
  *      dev_out: float32 [ntpl][nx][ns]. */
 int d4w_xcorr(d4w_fft_plan* plan, const float* dev_x, int nx, int ns, int valid, int ntpl, const void* dev_tabs,
@@ -134,7 +134,9 @@ int d4w_xcorr(d4w_fft_plan* plan, const float* dev_x, int nx, int ns, int valid,
               void* stream);
 
 /* ---- Hilbert envelope |scipy.signal.hilbert(x, axis=1)| (detect.py:192) and
- *      dsp.snr_tr_array(trace, env=True) (dsp.py:975).  mode 0: envelope, 1: 10*log10(env^2/var). */
+ *      dsp.snr_tr_array(trace, env=True) (dsp.py:975).  mode 0: envelope, 1: 10*log10(env^2/var).
+ *      dev_out must not overlap dev_x (long rows are transformed two per complex FFT and dev_x is read again at the end).
+ *      d4w_xcorr's dev_tabs are in d4w_fft_plan_table_order. */
 int d4w_row_plan_create(d4w_row_plan** out, int ns, int device);
 int d4w_row_plan_destroy(d4w_row_plan* plan);
 size_t d4w_row_workspace_bytes(const d4w_row_plan* plan, int nx);
