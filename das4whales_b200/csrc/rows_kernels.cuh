@@ -668,14 +668,14 @@ k_peak_levels(const float* __restrict__ x, int ns, float* bmax, float* bmin, flo
 
 // minimum over the run of samples <= v adjacent to position p on one side (DIR = -1 left, +1 right), v included
 template <int DIR>
-__device__ __forceinline__ float peak_side_min(const float* __restrict__ r, int ns, int p, float v, const float* __restrict__ bm,
+__host__ __device__ __forceinline__ float peak_side_min(const float* __restrict__ r, int ns, int p, float v, const float* __restrict__ bm,
                                                const float* __restrict__ bn, const float* __restrict__ sm, const float* __restrict__ sn,
                                                int nb1) {
     float m = v;
     int b = p / kPkB;
     // rest of p's own block
     if (DIR < 0) { for (int i = p - 1; i >= b * kPkB; --i) { const float u = r[i]; if (u > v) return m; m = fminf(m, u); } }
-    else { const int e = min(ns, (b + 1) * kPkB); for (int i = p + 1; i < e; ++i) { const float u = r[i]; if (u > v) return m; m = fminf(m, u); } }
+    else { const int e = ns < (b + 1) * kPkB ? ns : (b + 1) * kPkB; for (int i = p + 1; i < e; ++i) { const float u = r[i]; if (u > v) return m; m = fminf(m, u); } }
     b += DIR;
     while (b >= 0 && b < nb1) {
         const int sb = b / kPkB;
@@ -683,7 +683,7 @@ __device__ __forceinline__ float peak_side_min(const float* __restrict__ r, int 
         const bool sb_full = DIR < 0 ? true : ((sb + 1) * kPkB <= nb1);
         if (sb_edge && sb_full && !(sm[sb] > v)) { m = fminf(m, sn[sb]); b += DIR * kPkB; continue; }    // whole superblock <= v
         if (!(bm[b] > v)) { m = fminf(m, bn[b]); b += DIR; continue; }                                   // whole block <= v
-        const int lo = b * kPkB, hi = min(ns, lo + kPkB);
+        const int lo = b * kPkB, hi = ns < lo + kPkB ? ns : lo + kPkB;
         if (DIR < 0) { for (int i = hi - 1; i >= lo; --i) { const float u = r[i]; if (u > v) return m; m = fminf(m, u); } }
         else { for (int i = lo; i < hi; ++i) { const float u = r[i]; if (u > v) return m; m = fminf(m, u); } }
         b += DIR;                                          // only reached when the block's maximum is a NaN artefact
@@ -691,24 +691,32 @@ __device__ __forceinline__ float peak_side_min(const float* __restrict__ r, int 
     return m;
 }
 
+// index of the accepted peak whose flat top starts at sample i, or -1 (one call per sample; shared by the kernel and
+// the host emulation test)
+__host__ __device__ __forceinline__ int peak_pick_one(const float* __restrict__ r, int ns, int i, const float* __restrict__ bm,
+                                                      const float* __restrict__ bn, const float* __restrict__ sm,
+                                                      const float* __restrict__ sn, int nb1, float rowmin, double thr) {
+    if (i < 1 || i >= ns - 1) return -1;
+    const float v = r[i];
+    if (!(r[i - 1] < v)) return -1;
+    int e = i + 1;
+    while (e < ns - 1 && r[e] == v) ++e;
+    if (!(r[e] < v)) return -1;
+    if ((double)v - (double)rowmin < thr) return -1;                   // prominence <= height above the row minimum
+    const int p = (i + e - 1) / 2;
+    const float lmin = peak_side_min<-1>(r, ns, p, v, bm, bn, sm, sn, nb1);
+    const float rmin = peak_side_min<+1>(r, ns, p, v, bm, bn, sm, sn, nb1);
+    return ((double)v - (double)fmaxf(lmin, rmin) >= thr) ? p : -1;
+}
+
 static __global__ void __launch_bounds__(256)
 k_peak_pick(const float* __restrict__ x, int ns, PeakLevels lv, const float* __restrict__ rowmin, double thr, unsigned char* __restrict__ flags) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const size_t row = blockIdx.y;
-    if (i < 1 || i >= ns - 1) return;
-    const float* r = x + row * (size_t)ns;
-    const float v = r[i];
-    if (!(r[i - 1] < v)) return;
-    int e = i + 1;
-    while (e < ns - 1 && r[e] == v) ++e;
-    if (!(r[e] < v)) return;
-    if ((double)v - (double)rowmin[row] < thr) return;                 // prominence <= height above the row minimum
-    const int p = (i + e - 1) / 2;
-    const float* bm = lv.bmax + row * lv.nb1; const float* bn = lv.bmin + row * lv.nb1;
-    const float* sm = lv.smax + row * lv.nb2; const float* sn = lv.smin + row * lv.nb2;
-    const float lmin = peak_side_min<-1>(r, ns, p, v, bm, bn, sm, sn, lv.nb1);
-    const float rmin = peak_side_min<+1>(r, ns, p, v, bm, bn, sm, sn, lv.nb1);
-    if ((double)v - (double)fmaxf(lmin, rmin) >= thr) flags[row * (size_t)ns + p] = 1;
+    if (i >= ns) return;
+    const int p = peak_pick_one(x + row * (size_t)ns, ns, i, lv.bmax + row * lv.nb1, lv.bmin + row * lv.nb1, lv.smax + row * lv.nb2,
+                                lv.smin + row * lv.nb2, lv.nb1, rowmin[row], thr);
+    if (p >= 0) flags[row * (size_t)ns + p] = 1;
 }
 
 // ------------------------------------------------------------------ loader-side fusion: raw counts -> strain

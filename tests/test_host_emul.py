@@ -95,3 +95,26 @@ def test_fk_pipeline_emulation(tmpdir_mod):
             refh = O.fk_filter_filt(x64.copy(), Mh, tapering=taper)
             yh, _ = _run(exe, tmpdir_mod, nx, ns, 1, taper, x32, kval, fval, cc, H=H, col=(i0, i1), env=env)
             assert rel_err(yh, refh)[0] <= 5e-6, (nx, ns, "hybrid_ninf")
+
+
+def test_peak_picker_emulation(tmpdir_mod):
+    """The device peak picker's per-sample body (flat tops, hierarchical prominence walk over 64-sample blocks and
+    64-block superblocks) on the host against scipy.signal.find_peaks, index for index, on the same float32 rows."""
+    exe = _build("peaks_emul", tmpdir_mod)
+    rng = np.random.default_rng(17)
+    for ns in (2, 3, 5, 64, 65, 130, 4097, 9000):
+        rows = [rng.standard_normal(ns), np.abs(np.sin(np.arange(ns) * 0.01)) * (1 + 0.05 * rng.standard_normal(ns)),
+                np.round(rng.standard_normal(ns) * 2) / 2, np.full(ns, 1.5), np.arange(ns, dtype=np.float64),
+                -np.arange(ns, dtype=np.float64), np.concatenate([np.zeros(ns // 2), np.ones(ns - ns // 2)]),
+                np.where(np.arange(ns) % 7 == 3, 2.0, np.round(rng.standard_normal(ns)))]
+        x = np.stack(rows).astype(np.float32)
+        for thr in (0.0, 0.3, 1.0, 2.5):
+            fin, fout = os.path.join(tmpdir_mod, "pk.in"), os.path.join(tmpdir_mod, "pk.out")
+            with open(fin, "wb") as f:
+                f.write(struct.pack("<iid", x.shape[0], ns, thr))
+                f.write(x.tobytes())
+            subprocess.run([exe, fin, fout], check=True)
+            flags = np.frombuffer(open(fout, "rb").read(), dtype=np.uint8).reshape(x.shape)
+            for r in range(x.shape[0]):
+                ref = sps.find_peaks(x[r].astype(np.float64), prominence=thr)[0]
+                assert np.array_equal(np.nonzero(flags[r])[0], ref), (ns, thr, r)
