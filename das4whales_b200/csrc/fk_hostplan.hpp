@@ -68,7 +68,8 @@ inline int build_fk_hostplan(int nx, int ns, size_t smem_cap, FkHostPlan& hp, st
     const size_t col_budget = std::min<size_t>(smem_cap, 200 * 1024);
     while (nc > 1 && (size_t)nc * (nx + 1) * sizeof(float2) > col_budget) nc >>= 1;
     if ((size_t)nc * (nx + 1) * sizeof(float2) > smem_cap) {
-        err = "channel axis too long for one SM's shared memory (" + std::to_string(nx) + " channels); shard the matrix over GPUs";
+        err = "channel axis too long (" + std::to_string(nx) + " channels): one column of the wavenumber transform must fit one SM's "
+              "shared memory (about 28 000 channels); filter a channel sub-range or decimate the channel axis";
         return 1;
     }
     const int forced_nc = env_int("D4W_COL_NC", 0);

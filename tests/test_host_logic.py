@@ -74,3 +74,25 @@ def test_butterworth_and_taper_kat(golden):
     dw.dsp._taper_edges_inplace(y)
     import scipy.signal as sp
     assert np.array_equal(y, x * sp.windows.tukey(400, alpha=0.03)[None, :])
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs first) prints one JSON line with the agreed keys, and the
+    product arm refuses to run without a GPU instead of falling back to the CPU."""
+    import json, os, subprocess, sys
+    from conftest import ROOT
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-500:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["unit"] == "channels/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] == 1 and "sample" in line["cpu_baseline"]
+    assert line["e2e"]["value"] == line["value"] and line["e2e"]["h2d_bytes_per_step"] == 0
+    import torch
+    if not torch.cuda.is_available():
+        r2 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1"],
+                            capture_output=True, text=True, timeout=300)
+        assert r2.returncode != 0 and "{\"metric\"" not in r2.stdout
