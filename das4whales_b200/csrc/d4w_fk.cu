@@ -405,7 +405,8 @@ static bool launch_colB_fused(const d4w_fk_plan* pl, const Col2Params& c2, const
     const size_t smem = (size_t)pl->col2.np * pl->col2.fstride * sizeof(cpd);
 #define D4W_FUSED(RA, RB)                                                                                              \
     if (ra == RA && rb == RB) {                                                                                        \
-        static bool attr_done = false;   /* opt in to > 48 KB dynamic shared memory once per instantiation */          \
+        static bool attr_done_dev[64] = {};   /* opt in to > 48 KB dynamic shared memory once per instantiation and device */ \
+        bool& attr_done = attr_done_dev[pl->device & 63];                                                              \
         if (!attr_done) {                                                                                              \
             if constexpr (!INV) cudaFuncSetAttribute(k_colB_fwd_fused<RA, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
             else cudaFuncSetAttribute(k_colB_inv_fused<RA, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);               \
@@ -435,7 +436,8 @@ static int launch_col2_pipe(const d4w_fk_plan* pl, const d4w_fk_mask* m, const f
     bool done = false;
 #define D4W_PIPE(X1, RA, RB)                                                                                              \
     if (!done && x1 == X1 && ra == RA) {                                                                                  \
-        static bool attr_done = false;                                                                                    \
+        static bool attr_done_dev[64] = {};                                                                               \
+        bool& attr_done = attr_done_dev[pl->device & 63];                                                                 \
         if (!attr_done) { cudaFuncSetAttribute(k_col2_pipe<X1, RA, RB, INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_done = true; } \
         k_col2_pipe<X1, RA, RB, INV><<<grid, 160, smem, stream>>>(pl->col2, pp, x, y, v2, w, ldw, m->d_need, tap);        \
         done = true;                                                                                                      \
