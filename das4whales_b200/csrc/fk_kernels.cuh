@@ -547,24 +547,31 @@ __host__ __device__ inline void body_colA_fwd(const Col2Params& cp, const float*
     const size_t hp = (size_t)cp.vhp;
     const size_t tg = 4 * (size_t)(tpb / 2 + t4);      // first of this thread's four samples in the record
     cpd v[X1];
-    f2x ta = vbc(1.f), tb = vbc(1.f);
-    if (taper) { ta = f2x_set(taper[tg], taper[tg + 1]); tb = f2x_set(taper[tg + 2], taper[tg + 3]); }
     float2 twp[X1 / 2 + 1];                                          // W_nx^{c2 k1}, k1 = 0 .. X1/2, from one table read
     twiddle_powers<X1 / 2 + 1>(cp.twn[c2], twp);
+    // window (Tukey taper) of the four samples; 1.0 when not tapering: an unconditional multiply is exact and cheaper than
+    // selecting between tapered and untapered registers
+    f2x wa = vbc(1.f), wb = vbc(1.f);
+    if (taper) { wa = f2x_set(taper[tg], taper[tg + 1]); wb = f2x_set(taper[tg + 2], taper[tg + 3]); }
     static_for<X1>([&](auto c1c) {
         constexpr int c1 = decltype(c1c)::value;
         const float4 a = ld16<PIPE>(x + (size_t)(x2 * c1 + c2) * ns + tg, pol.stream);
-        v[c1] = dmake(f2x_set(a.x, a.y), f2x_set(a.z, a.w));
-        if (taper) { v[c1].x = vmul(v[c1].x, ta); v[c1].y = vmul(v[c1].y, tb); }
+        v[c1] = dmake(vmul(f2x_set(a.x, a.y), wa), vmul(f2x_set(a.z, a.w), wb));
     });
     DFTD<X1, false>::run(v);
     const f2x half = vbc(0.5f);
     static_for<X1 / 2 + 1>([&](auto kc) {
         constexpr int k1 = decltype(kc)::value;
         const cpd z = v[outpos<X1>(k1)], z2 = v[outpos<X1>((X1 - k1) % X1)];
-        cpd fa = dmake(vmul(vadd(z.x, z2.x), half), vmul(vsub(z.y, z2.y), half));     // lanes F_t, F_t+1
-        cpd fb = dmake(vmul(vadd(z.y, z2.y), half), vmul(vsub(z2.x, z.x), half));     // lanes F_t+2, F_t+3
-        if (k1 > 0) { const float2 w = twp[k1]; fa = dmul_s(fa, w); fb = dmul_s(fb, w); }
+        // F_t, F_t+1 (fa) and F_t+2, F_t+3 (fb) = halves of the sum / difference; the 1/2 rides on the twiddle for k1 > 0
+        cpd fa = dmake(vadd(z.x, z2.x), vsub(z.y, z2.y));
+        cpd fb = dmake(vadd(z.y, z2.y), vsub(z2.x, z.x));
+        if constexpr (k1 > 0) {
+            const float2 w = make_float2(0.5f * twp[k1].x, 0.5f * twp[k1].y);
+            fa = dmul_s(fa, w); fb = dmul_s(fb, w);
+        } else {
+            fa = dmake(vmul(fa.x, half), vmul(fa.y, half)); fb = dmake(vmul(fb.x, half), vmul(fb.y, half));
+        }
         cpd* o = v2 + ((size_t)k1 * x2 + c2) * hp + 2 * t4;
         stc<PIPE>(o, fa, pol.keep); stc<PIPE>(o + 1, fb, pol.keep);
     });
