@@ -96,3 +96,15 @@ def test_bench_reference_arm_contract():
         r2 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1"],
                             capture_output=True, text=True, timeout=300)
         assert r2.returncode != 0 and "{\"metric\"" not in r2.stdout
+
+
+def test_pick_list_helpers_match_oracle():
+    """convert_pick_times / select_picked_times are host-side list handling: same result as the restated reference."""
+    import das4whales_b200 as dw
+    from oracle import detect_oracle as D
+    picks = [np.array([3, 10, 11], dtype=np.int64), np.empty(0, dtype=np.int64), np.array([7], dtype=np.int64), np.empty(0, dtype=np.int64)]
+    got, ref = dw.detect.convert_pick_times(picks), D.convert_pick_times(picks)
+    assert got.shape == (2, 4) and np.array_equal(got, ref)
+    assert dw.detect.convert_pick_times([np.empty(0, dtype=np.int64)] * 3).shape == (2, 0)
+    sel = dw.detect.select_picked_times(got, 0.02, 0.055, 200.0)
+    assert np.array_equal(sel[0], [0, 0, 2]) and np.array_equal(sel[1], [10, 11, 7])
