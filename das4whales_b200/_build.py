@@ -10,7 +10,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libd4w.so")
-SOURCES = ["d4w_fk.cu", "d4w_rows.cu"]
+SOURCES = ["d4w_fk.cu", "d4w_rows.cu", "d4w_image.cu"]
 NVCC_FLAGS = ["-std=c++17", "-O3", "--expt-relaxed-constexpr", "-gencode", "arch=compute_100a,code=sm_100a",
               "-lineinfo", "-Xcompiler", "-fPIC", "-Wno-deprecated-gpu-targets"]
 
@@ -30,8 +30,20 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
+def _sync_header():
+    """Keep the in-package copy of the C header identical to include/d4w.h."""
+    src, dst = os.path.join(HERE, "..", "include", "d4w.h"), os.path.join(HERE, "d4w.h")
+    if os.path.exists(src):
+        with open(src, "rb") as f:
+            text = f.read()
+        if not os.path.exists(dst) or open(dst, "rb").read() != text:
+            with open(dst, "wb") as f:
+                f.write(text)
+
+
 def build_library(force=False, verbose=False):
     """Compile every .cu into one shared library. Returns the path of libd4w.so."""
+    _sync_header()
     if not force and not _stale():
         return LIB
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]

@@ -10,7 +10,10 @@ import threading
 import cffi
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-HEADER = os.path.normpath(os.path.join(HERE, "..", "include", "d4w.h"))
+# canonical header: <repo>/include/d4w.h; das4whales_b200/d4w.h is the copy that ships inside the package (refreshed by
+# _build.build_library, checked identical by tests/test_abi.py) so that an installed / copied package still imports
+_ROOT_HEADER = os.path.normpath(os.path.join(HERE, "..", "include", "d4w.h"))
+HEADER = _ROOT_HEADER if os.path.exists(_ROOT_HEADER) else os.path.join(HERE, "d4w.h")
 LIBPATH = os.path.join(HERE, "libd4w.so")
 
 ffi = cffi.FFI()

@@ -223,7 +223,8 @@ extern "C" int d4w_fk_plan_info(const d4w_fk_plan* pl, int* info) {
 }
 
 // ------------------------------------------------------------------------------- masks
-static int mask_finish_support(d4w_fk_mask* m, void* stream_v) {
+// eps_arg < 0: exact pruning unless the environment variable D4W_MASK_EPS says otherwise
+static int mask_finish_support(d4w_fk_mask* m, void* stream_v, double eps_arg = -1.0) {
     d4w_fk_plan* pl = m->plan;
     cudaStream_t stream = (cudaStream_t)stream_v;
     const int nrows = pl->nx / 2 + 1;
@@ -244,7 +245,9 @@ static int mask_finish_support(d4w_fk_mask* m, void* stream_v) {
     if (e != cudaSuccess) return fail(D4W_ERR_CUDA, std::string("mask support scan: ") + cudaGetErrorString(e));
     // exact pruning by default; D4W_MASK_EPS > 0 additionally drops rows whose folded mask never exceeds eps
     const char* eps_s = std::getenv("D4W_MASK_EPS");
-    const float eps = (eps_s && *eps_s) ? (float)std::atof(eps_s) : 0.0f;
+    const float eps = eps_arg >= 0.0 ? (float)eps_arg : (eps_s && *eps_s) ? (float)std::atof(eps_s) : 0.0f;
+    cudaFree(m->d_act_k); cudaFree(m->d_k2slot); cudaFree(m->d_slot_pos); cudaFree(m->d_plane_ptr); cudaFree(m->d_ents); cudaFree(m->d_need);
+    m->d_act_k = m->d_k2slot = nullptr; m->d_slot_pos = nullptr; m->d_plane_ptr = nullptr; m->d_ents = nullptr; m->d_need = nullptr;
     std::vector<int> k2slot((size_t)nrows, -1);
     m->act_k.clear();
     for (int k = 0; k < nrows; ++k) {
@@ -328,6 +331,14 @@ extern "C" int d4w_fk_mask_destroy(d4w_fk_mask* m) {
     cudaFree(m->d_h); cudaFree(m->d_act_k); cudaFree(m->d_k2slot); cudaFree(m->d_slot_pos); cudaFree(m->d_plane_ptr); cudaFree(m->d_ents); cudaFree(m->d_need);
     delete m;
     return D4W_OK;
+}
+
+extern "C" int d4w_fk_mask_prune(d4w_fk_mask* m, double eps, void* stream) {
+    if (!m) return fail(D4W_ERR_ARG, "d4w_fk_mask_prune: null mask");
+    if (!(eps >= 0.0)) return fail(D4W_ERR_ARG, "d4w_fk_mask_prune: eps must be >= 0");
+    DeviceGuard guard(m->device);
+    m->d_table = nullptr;                       // the transform-order table must be rebuilt for the new support
+    return mask_finish_support(m, stream, eps);
 }
 
 extern "C" int d4w_fk_mask_rows(const d4w_fk_mask* m) { return m ? m->nact : 0; }
@@ -470,7 +481,12 @@ extern "C" int d4w_fk_apply_pass_ex(d4w_fk_plan* pl, d4w_fk_mask* m, const float
     const int tile = pl->col.dual ? 4 * pl->col.npair : 2 * pl->col.nc;
     const int ntiles = (pl->ns + tile - 1) / tile;
     const float* tap = taper ? mp->d_taper + t_offset : nullptr;
-    const bool two = pl->two_level && pl == mp && m->d_ents && ((uintptr_t)ws % 16 == 0);
+    // the per-plane tables of the mask were built for its own plan; a time-slab plan of the same channel axis has the very
+    // same two-level split (it depends on nx only), so the slab runs the two-level / pipelined kernels as well
+    const bool same_split = pl == mp || (pl->nx == mp->nx && pl->two_level && mp->two_level && pl->col2.x1 == mp->col2.x1 &&
+                                         pl->col2.x2 == mp->col2.x2 && pl->hostplan.fused_ra == mp->hostplan.fused_ra &&
+                                         pl->hostplan.fused_rb == mp->hostplan.fused_rb && pl->hostplan.pos_x2 == mp->hostplan.pos_x2);
+    const bool two = pl->two_level && same_split && m->d_ents && ((uintptr_t)ws % 16 == 0);
     cpd* v2 = nullptr;
     if (two) {
         size_t wb = std::max<size_t>((size_t)nact * pl->ns * sizeof(float2), 16);

@@ -200,7 +200,8 @@ extern "C" size_t d4w_row_workspace_bytes(const d4w_row_plan* p, int nx) {
 extern "C" int d4w_hilbert(d4w_row_plan* p, const float* x, float* out, int nx, void* workspace, int mode,
                            const double* dev_stats, void* stream_v) {
     if (!p || !x || !out || nx < 1) return fail(D4W_ERR_ARG, "d4w_hilbert: bad argument");
-    if (mode == EPI_SNR && !dev_stats) return fail(D4W_ERR_ARG, "d4w_hilbert: SNR mode needs row statistics");
+    if (mode < 0 || mode > EPI_ENVSTD) return fail(D4W_ERR_ARG, "d4w_hilbert: mode must be 0..3");
+    if ((mode == EPI_SNR || mode == EPI_ENVSTD) && !dev_stats) return fail(D4W_ERR_ARG, "d4w_hilbert: this mode needs row statistics");
     if (nx > 65535 && p->t1 > 1) return fail(D4W_ERR_UNSUPPORTED, "d4w_hilbert: more than 65535 rows per call");
     DeviceGuard guard(p->device);
     cudaStream_t stream = (cudaStream_t)stream_v;
@@ -319,6 +320,19 @@ extern "C" int d4w_stft_mag(d4w_fft_plan* p, const float* x, float* out, int nx,
     dim3 grid((sp.nframes + fpb - 1) / fpb, nx);
     k_stft_mag<<<grid, 256, smem, (cudaStream_t)stream_v>>>(sp, x, dev_window, out);
     D4W_CHECK_LAUNCH("k_stft_mag");
+    return D4W_OK;
+}
+
+// ------------------------------------------------------------------ per-channel FFT magnitude (dsp.get_fx)
+extern "C" int d4w_row_fft_mag(d4w_fft_plan* p, const float* x, int nx, size_t ld, int ncopy, double scale, float* out, void* stream_v) {
+    if (!p || !x || !out || nx < 1 || ncopy < 0) return fail(D4W_ERR_ARG, "d4w_row_fft_mag: bad argument");
+    if (ncopy > p->n) ncopy = p->n;                      // numpy.fft.fft(a, n) crops rows longer than n
+    const size_t smem = (size_t)p->n * sizeof(float2);
+    if (smem > p->smem_cap) return fail(D4W_ERR_UNSUPPORTED, "d4w_row_fft_mag: nfft too large for shared memory (max ~28 000)");
+    DeviceGuard guard(p->device);
+    D4W_CUDA_TRY(cudaFuncSetAttribute(k_row_fftmag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_cap));
+    k_row_fftmag<<<nx, 256, smem, (cudaStream_t)stream_v>>>(p->pl, p->d_tw, p->d_k2pos, x, ld, ncopy, (float)scale, out);
+    D4W_CHECK_LAUNCH("k_row_fftmag");
     return D4W_OK;
 }
 

@@ -273,10 +273,14 @@ k_xcorr_fused(XcorrParams xp, const float* __restrict__ x, const float2* __restr
 }
 
 // ------------------------------------------------------------------ Hilbert envelope / SNR on the T1 x T2 row engine
-enum { EPI_ENV = 0, EPI_SNR = 1 };
+// EPI_HILB: the Hilbert transform H(x) itself (dsp.instant_freq needs the phase); EPI_ENVSTD: envelope / std_row
+// (improcess.trace2image, improcess.py:61)
+enum { EPI_ENV = 0, EPI_SNR = 1, EPI_HILB = 2, EPI_ENVSTD = 3 };
 
 __device__ __forceinline__ float hilbert_epilogue(float2 z, int mode, float var) {
+    if (mode == EPI_HILB) return z.y;
     const float p = z.x * z.x + z.y * z.y;
+    if (mode == EPI_ENVSTD) return sqrtf(p) / sqrtf(var);
     return mode == EPI_ENV ? sqrtf(p) : 10.0f * log10f(p / var);
 }
 
@@ -315,7 +319,7 @@ k_hsplit_inv(const float2* __restrict__ w, int ns, float* __restrict__ out, int 
     twiddle_powers<T1>(twT[t2], p);
     static_for<T1>([&](auto jc) { constexpr int j = decltype(jc)::value; if constexpr (j > 0) v[j] = cmulc(v[j], p[j]); });
     DFT<T1, true>::run(v);
-    const float var = (mode == EPI_SNR) ? (float)stats[4 * row + 2] : 1.f;
+    const float var = (mode == EPI_SNR || mode == EPI_ENVSTD) ? (float)stats[4 * row + 2] : 1.f;
     float* dst = out + row * ns + t2;
     static_for<T1>([&](auto jc) { constexpr int j = decltype(jc)::value; dst[(size_t)j * t2len] = hilbert_epilogue(v[j], mode, var); });
 }
@@ -326,7 +330,9 @@ k_hsplit_inv(const float2* __restrict__ w, int ns, float* __restrict__ out, int 
 // pass multiplies by the real table sgn(f)/ns (0 at DC and Nyquist, scipy.signal.hilbert's h - 1); the factor -i is
 // applied here: with u = IFFT(Z sgn), H(a) = Im u and H(b) = -Re u; |hilbert(a)| = sqrt(a^2 + H(a)^2).
 __device__ __forceinline__ float hilbert_epilogue2(float x, float h, int mode, float var) {
+    if (mode == EPI_HILB) return h;
     const float p = x * x + h * h;
+    if (mode == EPI_ENVSTD) return sqrtf(p) / sqrtf(var);
     return mode == EPI_ENV ? sqrtf(p) : 10.0f * log10f(p / var);
 }
 template <int T1>
@@ -368,8 +374,9 @@ k_hsplit_inv2(const float2* __restrict__ w, const float* __restrict__ x, int nx,
     DFT<T1, true>::run(v);
     const size_t ra = 2 * pr, rb = 2 * pr + 1;
     const bool has_b = rb < (size_t)nx;
-    const float va = (mode == EPI_SNR) ? (float)stats[4 * ra + 2] : 1.f;
-    const float vb = (mode == EPI_SNR && has_b) ? (float)stats[4 * rb + 2] : 1.f;
+    const bool need_var = mode == EPI_SNR || mode == EPI_ENVSTD;
+    const float va = need_var ? (float)stats[4 * ra + 2] : 1.f;
+    const float vb = (need_var && has_b) ? (float)stats[4 * rb + 2] : 1.f;
     const float* xa = x + ra * ns + t2;
     float* oa = out + ra * ns + t2;
     static_for<T1>([&](auto jc) {
@@ -394,9 +401,30 @@ k_hilbert_row(RowParams rp, const float* __restrict__ x, float* __restrict__ out
     for (int i = tid; i < n; i += nthr) { const float s = tab[i]; float2 v = sm[i]; v.x *= s; v.y *= s; sm[i] = v; }
     __syncthreads();
     fft_inverse_stages(sm, rp.pl, rp.tw, 1, n, tid, nthr, 0, rp.pl.nstages);
-    const float var = (mode == EPI_SNR) ? (float)stats[4 * row + 2] : 1.f;
+    const float var = (mode == EPI_SNR || mode == EPI_ENVSTD) ? (float)stats[4 * row + 2] : 1.f;
     float* dst = out + row * n;
     for (int i = tid; i < n; i += nthr) dst[i] = hilbert_epilogue(sm[i], mode, var);
+}
+
+// ------------------------------------------------------------------ per-channel FFT magnitude (dsp.get_fx, dsp.py:18-38)
+// one CTA per row: x[row][0:ncopy] zero-padded to n -> FFT -> out[row][(f + n/2) % n] = |X[f]| * scale (np.fft.fftshift order)
+static __global__ void __launch_bounds__(256, 2)
+k_row_fftmag(FftPlan pl, const float2* __restrict__ tw, const int* __restrict__ k2pos, const float* __restrict__ x, size_t ld,
+             int ncopy, float scale, float* __restrict__ out) {
+    extern __shared__ float2 sm[];
+    const int n = pl.n, tid = threadIdx.x, nthr = blockDim.x;
+    const size_t row = blockIdx.x;
+    const float* src = x + row * ld;
+    for (int i = tid; i < n; i += nthr) sm[i] = make_float2(i < ncopy ? src[i] : 0.f, 0.f);
+    __syncthreads();
+    fft_forward_stages(sm, pl, tw, 1, n, tid, nthr, 0, pl.nstages);
+    float* dst = out + row * (size_t)n;
+    const int half = n / 2;
+    for (int j = tid; j < n; j += nthr) {
+        int f = j - half; if (f < 0) f += n;                  // shifted index j holds frequency (j - n//2) mod n
+        const float2 v = sm[k2pos[f]];
+        dst[j] = sqrtf(v.x * v.x + v.y * v.y) * scale;
+    }
 }
 
 // ------------------------------------------------------------------ forward-backward SOS IIR (scipy sosfiltfilt semantics)

@@ -30,18 +30,45 @@ def gen_template_fincall(time, fs, fmin=15., fmax=25., duration=1., window=True)
     return template
 
 
+def _host1d(a):
+    if _is_tensor(a):
+        return a.detach().to("cpu").numpy().astype(np.float64).ravel()
+    return np.asarray(a, dtype=np.float64).ravel()
+
+
+def _lags_on_device(x_dev, y_host):
+    """z[tau] = sum_n x[n + tau] y[n] for tau = 0 .. len(x) - 1 (float32 CUDA tensor), y = FIR taps on the host."""
+    return _rows.cross_correlogram(x_dev, [y_host], normalize=False)[0][0]
+
+
 def shift_xcorr(x, y):
-    """Positive-lag cross-correlation of two 1-D arrays (reference: detect.py:96-112)."""
-    x = np.asarray(x, dtype=np.float64)
-    out = _rows.cross_correlogram(_to_device(x[None, :]), [np.asarray(y, dtype=np.float64)], normalize=False)[0]
-    return _to_host64(out)[0]
+    """`scipy.signal.correlate(x, y, 'full', 'fft')[len(x) - 1:]` (reference: detect.py:96-112): len(y) values, lag
+    tau_j = len(x) - len(y) + j.  For equal lengths (the reference's use) these are the positive lags 0 .. len(x) - 1;
+    for unequal lengths the same slice of the full correlation is returned, negative lags included.
+    ndarray in -> float64 ndarray out; CUDA tensor in -> float32 CUDA tensor out."""
+    import torch
+    tens = _is_tensor(x)
+    xh = None if tens else np.asarray(x, dtype=np.float64).ravel()
+    xd = (x.reshape(1, -1).to(torch.float32).contiguous() if tens else _to_device(xh[None, :]))
+    yh = _host1d(y)
+    nx_, ny_ = xd.shape[1], len(yh)
+    zpos = _lags_on_device(xd, yh)                                 # lags 0 .. nx_-1
+    first = nx_ - ny_                                              # lag of the first returned sample
+    if first >= 0:
+        out = zpos[first:first + ny_]
+    else:
+        # negative lags: z_xy[-m] = z_yx[m] -- correlate y (as the signal) against x (as the taps)
+        yd = torch.from_numpy(yh.astype(np.float32))[None, :].to(xd.device)
+        xtaps = _host1d(x)
+        zneg = _lags_on_device(yd, xtaps)                          # z_yx[m], m = 0 .. ny_-1
+        out = torch.cat((torch.flip(zneg[1:-first + 1], dims=(0,)), zpos))[:ny_]
+    return out if tens else out.to(torch.float64).cpu().numpy()
 
 
 def shift_nxcorr(x, y):
-    """Std-normalised positive-lag cross-correlation (reference: detect.py:115-137)."""
-    x = np.asarray(x, dtype=np.float64)
-    y = np.asarray(y, dtype=np.float64)
-    return shift_xcorr(x, y) / (np.std(x) * np.std(y) * len(x))
+    """Std-normalised cross-correlation, same lags as shift_xcorr (reference: detect.py:115-137)."""
+    xh, yh = _host1d(x), _host1d(y)
+    return shift_xcorr(x, y) / (np.std(xh) * np.std(yh) * len(xh))
 
 
 def compute_cross_correlogram(data, template):
@@ -49,14 +76,14 @@ def compute_cross_correlogram(data, template):
     rows demeaned and divided by their raw abs-max, template (zero-padded to ns) demeaned and
     divided by its abs-max, positive lags of the full correlation."""
     xd = _to_device(data)
-    out = _rows.cross_correlogram(xd, [np.asarray(template, dtype=np.float64)], normalize=True)[0]
+    out = _rows.cross_correlogram_chunked(xd, [np.asarray(template, dtype=np.float64)], normalize=True)[0]
     return out if _is_tensor(data) else _to_host64(out)
 
 
 def compute_cross_correlograms(data, templates):
     """Several templates in ONE pass over the data (HF + LF notes of scripts/main_mfdetect.py:79-80)."""
     xd = _to_device(data)
-    outs = _rows.cross_correlogram(xd, [np.asarray(t, dtype=np.float64) for t in templates], normalize=True)
+    outs = _rows.cross_correlogram_chunked(xd, [np.asarray(t, dtype=np.float64) for t in templates], normalize=True)
     return outs if _is_tensor(data) else [_to_host64(o) for o in outs]
 
 
@@ -78,7 +105,17 @@ def pick_times(corr_m, threshold):
     return _rows.find_peaks(_to_device(corr_m), float(threshold))
 
 
-pick_times_par = pick_times_env
+def process_corr(corr, threshold):
+    """Peak indexes of ONE correlation series: find_peaks(|hilbert(corr)|, prominence=threshold)[0]
+    (reference: detect.py:198-218, the per-channel kernel of pick_times_par)."""
+    c = corr.reshape(1, -1) if _is_tensor(corr) else np.asarray(corr)[None, :]
+    return pick_times_env(c, threshold)[0]
+
+
+def pick_times_par(corr_m, threshold):
+    """Reference: detect.py:221-246 (a thread pool over process_corr whose results arrive in completion order).  All
+    channels are picked in one batched GPU pass; the list is returned in channel order, like pick_times_env."""
+    return pick_times_env(corr_m, threshold)
 
 
 def convert_pick_times(peaks_indexes_m):
@@ -154,6 +191,45 @@ def xcorr2d(spectro, kernel):
         S = torch.from_numpy(np.ascontiguousarray(spectro, dtype=np.float32)).cuda()[None]
     out = _rows.spectro_correlate(S, kernel)[0]
     return out if _is_tensor(spectro) else out.to(torch.float64).cpu().numpy()
+
+
+def nxcorr2d(spectro, kernel):
+    """max over frequency lags of the normalised 2-D cross-correlation (reference: detect.py:544-576):
+    scipy.signal.correlate(spectro, kernel, 'same') / (std(spectro) std(kernel) n_time) -> max over axis 0."""
+    import torch
+    from . import improcess as _imp
+    tens = _is_tensor(spectro)
+    S = spectro.to(torch.float32).contiguous() if tens else torch.from_numpy(np.ascontiguousarray(spectro, dtype=np.float32)).cuda()
+    K = np.ascontiguousarray(_host2d(kernel), dtype=np.float64)
+    corr = _imp.filter2D(S, None, K, border="zeros")
+    s_std = float(S.to(torch.float64).std(unbiased=False).item())
+    out = corr.max(dim=0).values / (s_std * float(np.std(K)) * S.shape[1])
+    return out if tens else out.to(torch.float64).cpu().numpy()
+
+
+def _host2d(a):
+    if _is_tensor(a):
+        return a.detach().to("cpu").numpy()
+    return np.asarray(a)
+
+
+def xcorr(t, f, Sxx, tvec, fvec, BlueKernel):
+    """Sliding dot product of a kernel with a spectrogram ('valid' lags), normalised by median(Sxx) * len(tvec), first and
+    last value zeroed, negatives clipped (reference: detect.py:605-647).  Returns [t_scale, CorrVal]."""
+    import torch
+    tvec_size, fvec_size = int(np.size(tvec)), int(np.size(fvec))
+    tens = _is_tensor(Sxx)
+    S = Sxx.to(torch.float32).contiguous() if tens else torch.from_numpy(np.ascontiguousarray(Sxx, dtype=np.float32)).cuda()
+    nt = S.shape[1]
+    nval = nt - (tvec_size - 1)
+    med = _rows.row_median(S.reshape(1, -1))                       # median over the WHOLE spectrogram (detect.py:642)
+    same = _rows.spectro_correlate(S[:fvec_size][None].contiguous(), _host2d(BlueKernel), median=med)[0]
+    corr = same[tvec_size // 2: tvec_size // 2 + nval].clone()     # 'valid' lags of the 'same'-mode correlation
+    corr[0] = 0
+    corr[-1] = 0
+    t = np.asarray(t)
+    t_scale = t[int(tvec_size / 2) - 1:-int(np.ceil(tvec_size / 2))]
+    return [t_scale, corr if tens else corr.to(torch.float64).cpu().numpy()]
 
 
 def compute_cross_correlogram_spectrocorr(data, fs, flims, kernel, win_size, overlap_pct):

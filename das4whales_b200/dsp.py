@@ -295,16 +295,20 @@ def get_spectrogram(waveform, fs, nfft=128, overlap_pct=0.8):
 
 
 def get_fx(trace, nfft):
-    """Per-channel FFT magnitude view (reference: dsp.py:18-38).  Plot helper, host NumPy."""
-    fx = 2 * (abs(np.fft.fftshift(np.fft.fft(np.asarray(trace), nfft), axes=1)))
-    fx /= nfft
-    fx *= 10 ** 9
-    return fx
+    """Per-channel FFT magnitude in nano-strain, fftshift-ed along frequency (reference: dsp.py:18-38):
+    2 |fft(trace, nfft)| / nfft * 1e9 -- one shared-memory FFT per channel on the GPU (d4w_row_fft_mag)."""
+    xd = _to_device(trace)
+    fx = _rows.row_fft_mag(xd, int(nfft), 2.0e9 / int(nfft))
+    return fx if _is_tensor(trace) else _to_host64(fx)
 
 
 def instant_freq(channel, fs):
-    """Instantaneous frequency of one channel (reference: dsp.py:830-856).  Plot helper."""
-    return np.diff(np.unwrap(np.angle(sp.hilbert(channel)))) / (2.0 * np.pi) * fs
+    """Instantaneous frequency of one channel, diff(unwrap(angle(hilbert(x)))) / 2 pi * fs (reference: dsp.py:830-856):
+    Hilbert transform on the row engine (d4w_hilbert mode 2), phase difference + numpy.unwrap's wrapping on the device."""
+    torch = _fk._torch()
+    xd = _to_device(channel.reshape(1, -1) if _is_tensor(channel) else np.asarray(channel).reshape(1, -1))
+    fi = _rows.inst_freq(xd[0], float(fs))
+    return fi if _is_tensor(channel) else fi.to(torch.float64).cpu().numpy()
 
 
 def snr_tr_array(trace, env=False):

@@ -14,6 +14,7 @@ from . import _lib
 
 _plan_cache = {}
 _plan_lock = threading.Lock()
+_plan_serial = [0]      # every _Plan gets a unique, never re-used serial (ids of freed objects can be re-used)
 
 
 def _torch():
@@ -31,6 +32,12 @@ class _Plan:
         out = _lib.ffi.new("d4w_fk_plan**")
         _lib.check(L.d4w_fk_plan_create(out, int(nx), int(ns), int(device)), f"fk plan {nx}x{ns}")
         self.ptr = out[0]
+        # the C plan lives exactly as long as this object: device masks keep a strong reference to their plan, so a
+        # d4w_fk_mask can never outlive the d4w_fk_plan it points to (free_plans() only empties the cache)
+        weakref.finalize(self, L.d4w_fk_plan_destroy, self.ptr)
+        with _plan_lock:
+            _plan_serial[0] += 1
+            self.serial = _plan_serial[0]
         self.nx, self.ns, self.device = int(nx), int(ns), int(device)
         info = _lib.ffi.new("int[8]")
         _lib.check(L.d4w_fk_plan_info(self.ptr, info), "fk plan info")
@@ -50,25 +57,27 @@ def get_plan(nx, ns, device):
     key = (int(nx), int(ns), int(device))
     with _plan_lock:
         p = _plan_cache.get(key)
-        if p is None:
-            p = _Plan(*key)
-            _plan_cache[key] = p
-        return p
+    if p is None:
+        p = _Plan(*key)
+        with _plan_lock:
+            p = _plan_cache.setdefault(key, p)
+    return p
 
 
 def free_plans():
-    """Drop every cached plan and its workspace."""
+    """Empty the plan cache (and the dense-mask cache).  A plan (and its workspace) is destroyed when the last
+    FkFilter / device mask that uses it is gone, so outstanding objects stay valid."""
     with _plan_lock:
-        L = _lib.lib()
         for p in _plan_cache.values():
-            L.d4w_fk_plan_destroy(p.ptr)
+            p.workspace = None
         _plan_cache.clear()
+    _dense_cache.clear()
 
 
 class _DeviceMask:
     """d4w_fk_mask handle + its transform-order table for one plan."""
 
-    def __init__(self, plan, create):
+    def __init__(self, plan, create, eps=0.0):
         torch = _torch()
         L = _lib.lib()
         self.plan = plan
@@ -76,6 +85,8 @@ class _DeviceMask:
         with torch.cuda.device(plan.device):
             create(L, out, plan)
             self.ptr = out[0]
+            if eps and eps > 0:
+                _lib.check(L.d4w_fk_mask_prune(self.ptr, float(eps), _lib.stream_ptr()), "fk mask prune")
             self.rows = L.d4w_fk_mask_rows(self.ptr)
             nbytes = L.d4w_fk_mask_table_bytes(self.ptr)
             self.table = torch.empty(int(nbytes) // 4, dtype=torch.float32, device=f"cuda:{plan.device}")
@@ -96,6 +107,7 @@ class FkMask:
         self.shape = (int(shape[0]), int(shape[1]))
         self.params = params
         self.order = order
+        self.prune_eps = 0.0           # opt-in: FkFilter / fk_filter_filt drop rows whose folded mask never exceeds this
         self.ndim = 2
         self.dtype = np.dtype(np.float64)
         self._dev = {}
@@ -116,16 +128,29 @@ class FkMask:
         else:
             raise ValueError(f"unknown analytic mask kind {self.kind}")
 
-    def on_device(self, plan):
-        dm = self._dev.get(id(plan))
+    def on_device(self, plan, eps=0.0):
+        eps = float(eps or 0.0)
+        if eps:
+            key = (plan.serial, eps)
+            dm = self._dev.get(key)
+            if dm is None:
+                if self.kind == "dense":
+                    dm = _DenseMaskHolder(plan, _dense_to_device(self._dense, plan.device), eps).dm
+                else:
+                    dm = _DeviceMask(plan, self._create, eps)
+                self._dev[key] = dm
+            return dm
+        dm = self._dev.get(plan.serial)
         if dm is None:
+            for k in [k for k, v in self._dev.items() if _plan_cache.get((v.plan.nx, v.plan.ns, v.plan.device)) is not v.plan]:
+                del self._dev[k]                      # tables of plans that were dropped by free_plans()
             if (plan.nx, plan.ns) != self.shape:
                 raise ValueError(f"operands could not be broadcast together with shapes ({plan.nx},{plan.ns}) {self.shape}")
             if self.kind == "dense":      # design functions without a closed form on the device
                 dm = _DenseMaskHolder(plan, _dense_to_device(self._dense, plan.device)).dm
             else:
                 dm = _DeviceMask(plan, self._create)
-            self._dev[id(plan)] = dm
+            self._dev[plan.serial] = dm
         return dm
 
     @classmethod
@@ -169,13 +194,13 @@ class FkMask:
 class _DenseMaskHolder:
     """Device state for a caller-supplied dense mask (ndarray / sparse.COO / tensor)."""
 
-    def __init__(self, plan, mask_dev):
+    def __init__(self, plan, mask_dev, eps=0.0):
         self.mask_dev = mask_dev      # float32 [nx, ns] shifted layout, kept alive for the support scan only
 
         def create(L, out, plan_):
             _lib.check(L.d4w_fk_mask_create_dense(out, plan_.ptr, _lib.ptr(mask_dev, "float*"), _lib.stream_ptr()),
                        "dense mask")
-        self.dm = _DeviceMask(plan, create)
+        self.dm = _DeviceMask(plan, create, eps)
         _torch().cuda.current_stream().synchronize()
         self.mask_dev = None          # the transform-order table is all the filter needs
 
@@ -199,23 +224,51 @@ def _dense_to_device(mask, device):
     return out
 
 
-def device_mask_for(mask, plan):
+def _fingerprint(mask):
+    """Cheap content fingerprint of a caller-owned dense mask: the cached device table is only re-used while the
+    array still holds the values it was built from (callers may refill / scale a mask array in place)."""
+    torch = _torch()
+    if isinstance(mask, torch.Tensor):
+        flat = mask.reshape(-1)
+        n = flat.numel()
+        step = max(1, n // 65536) | 1
+        samp = flat[::step].to(torch.float64)
+        return ("t", tuple(mask.shape), str(mask.dtype), int(mask.data_ptr()), int(mask._version),
+                float(samp.sum().item()), float((samp * samp).sum().item()))
+    if isinstance(mask, np.ndarray):
+        n = mask.size
+        step = max(1, n // 65536) | 1
+        samp = np.asarray(mask.reshape(-1, order="A")[::step], dtype=np.float64) if (mask.flags.c_contiguous or mask.flags.f_contiguous) \
+            else np.asarray(mask[::max(1, mask.shape[0] // 64)], dtype=np.float64).ravel()
+        return ("n", mask.shape, mask.dtype.str, mask.__array_interface__["data"][0], mask.strides,
+                float(samp.sum()), float(np.dot(samp, samp)))
+    data = getattr(mask, "data", None)           # sparse.COO: fingerprint the stored values
+    if isinstance(data, np.ndarray):
+        return ("s", tuple(mask.shape), data.size, float(np.sum(data[::max(1, data.size // 65536) | 1], dtype=np.float64)))
+    return None
+
+
+def device_mask_for(mask, plan, eps=0.0):
     """Resolve any accepted mask object to a _DeviceMask for `plan`."""
     if isinstance(mask, FkMask):
-        return mask.on_device(plan)
+        return mask.on_device(plan, eps if eps else getattr(mask, "prune_eps", 0.0))
+    if eps:
+        return _DenseMaskHolder(plan, _dense_to_device(mask, plan.device), float(eps)).dm
     shape = tuple(getattr(mask, "shape", ()))
     if shape != (plan.nx, plan.ns):
         raise ValueError(f"operands could not be broadcast together with shapes ({plan.nx},{plan.ns}) {shape}")
-    key = (id(mask), id(plan))
+    key = (id(mask), plan.serial)
+    fp = _fingerprint(mask)
     hit = _dense_cache.get(key)
-    if hit is not None and hit[0]() is mask:
+    if hit is not None and fp is not None and hit[0]() is mask and hit[2] == fp:
         return hit[1].dm
     holder = _DenseMaskHolder(plan, _dense_to_device(mask, plan.device))
-    try:
-        ref = weakref.ref(mask, lambda _r, k=key: _dense_cache.pop(k, None))
-        _dense_cache[key] = (ref, holder)
-    except TypeError:
-        pass
+    if fp is not None:
+        try:
+            ref = weakref.ref(mask, lambda _r, k=key: _dense_cache.pop(k, None))
+            _dense_cache[key] = (ref, holder, fp)
+        except TypeError:
+            pass
     return holder.dm
 
 
@@ -226,13 +279,15 @@ class FkFilter:
     >>> y = flt(x_cuda)                         # x_cuda: float32 CUDA tensor [nx, ns]
     """
 
-    def __init__(self, mask, shape=None, device=None):
+    def __init__(self, mask, shape=None, device=None, eps=0.0):
+        """eps > 0: opt-in approximate support pruning (d4w_fk_mask_prune): wavenumber rows whose folded mask never
+        exceeds eps are dropped; l2 error <= eps * ||x||.  A mask object may also carry the setting as `mask.prune_eps`."""
         torch = _torch()
         self.device = torch.cuda.current_device() if device is None else int(device)
         shape = tuple(shape) if shape is not None else tuple(mask.shape)
         self.plan = get_plan(shape[0], shape[1], self.device)
         with torch.cuda.device(self.device):
-            self.dm = device_mask_for(mask, self.plan)
+            self.dm = device_mask_for(mask, self.plan, eps)
         self.mask = mask
         self.rows_kept = self.dm.rows
 

@@ -80,11 +80,13 @@ def row_stats(x, seglen=0):
 
 
 # ------------------------------------------------------------------------------ matched filter
-def _pick_block(L):
+def _pick_block(L, ns=0):
     """Overlap-save block length.  Lengths of the form 2^a * 25 * 25 end in odd-radix stages, which keeps the
     8-byte shared-memory accesses of the last stages conflict-free (a power of two would end in a stride-16
     radix-16 stage: 6x the wavefronts); 2500 keeps three CTAs per SM with 94 % of each block valid."""
     for nb in (1250, 2500, 5000, 10000):
+        if ns and (ns + (nb - L)) // (nb - L + 1) > 512 and nb < 10000:
+            continue                                  # row statistics keep at most 512 segment prefixes per row
         if nb >= 8 * L or (nb == 10000 and nb >= L + 1):
             return nb
     raise ValueError(f"template with {L} taps is too long for the overlap-save matched filter (max 9999)")
@@ -114,7 +116,7 @@ def cross_correlogram(x, templates, normalize=True):
         else:
             taps.append(c); mus.append(0.0); ms.append(1.0)
     Lmax = max(len(c) for c in taps)
-    nb = _pick_block(Lmax)
+    nb = _pick_block(Lmax, ns)
     valid = nb - Lmax + 1
     plan = fft_plan(nb, dev)
     tabs = np.empty((len(taps), nb), dtype=np.complex64)
@@ -134,6 +136,23 @@ def cross_correlogram(x, templates, normalize=True):
         _lib.check(_lib.lib().d4w_xcorr(plan.ptr, _lib.ptr(x, "float*"), nx, ns, valid, len(taps), _lib.ptr(tabs_d),
                                         a_mu, a_st, a_sp, _lib.ptr(out, "float*"), _lib.stream_ptr()), "xcorr")
     return [out[i] for i in range(len(taps))]
+
+
+_MAX_ROWS = 65535       # gridDim.y limit of the row kernels
+
+
+def cross_correlogram_chunked(x, templates, normalize=True):
+    """cross_correlogram for any number of rows (the kernels take <= 65535 rows per launch)."""
+    torch = _torch()
+    nx = x.shape[0]
+    if nx <= _MAX_ROWS:
+        return cross_correlogram(x, templates, normalize)
+    outs = [torch.empty_like(x) for _ in templates]
+    for r0 in range(0, nx, _MAX_ROWS):
+        part = cross_correlogram(x[r0:r0 + _MAX_ROWS], templates, normalize)
+        for o, p in zip(outs, part):
+            o[r0:r0 + _MAX_ROWS] = p
+    return outs
 
 
 # ------------------------------------------------------------------------------ Hilbert envelope / SNR
@@ -160,6 +179,43 @@ def _hilbert(x, mode, stats=None):
 def envelope(x):
     """|scipy.signal.hilbert(x, axis=1)|"""
     return _hilbert(x, 0)
+
+
+def hilbert_imag(x):
+    """imag(scipy.signal.hilbert(x, axis=1)) = the Hilbert transform H(x) of every row"""
+    return _hilbert(x, 2)
+
+
+def envelope_over_std(x):
+    """|hilbert(x)| / std_row(x)  (improcess.trace2image before the pixel scaling, improcess.py:61)"""
+    stats, _ = row_stats(x)
+    return _hilbert(x, 3, stats)
+
+
+def row_fft_mag(x, nfft, scale):
+    """|numpy.fft.fft(x, nfft)| * scale in fftshift order for every row (dsp.get_fx, dsp.py:35-37)."""
+    torch = _torch()
+    dev = _check_input(x)
+    nx, ns = x.shape
+    plan = fft_plan(int(nfft), dev)
+    out = torch.empty((nx, int(nfft)), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().d4w_row_fft_mag(plan.ptr, _lib.ptr(x, "float*"), nx, ns, min(ns, int(nfft)), float(scale),
+                                              _lib.ptr(out, "float*"), _lib.stream_ptr()), "row_fft_mag")
+    return out
+
+
+def inst_freq(x1d, fs):
+    """dsp.instant_freq for one channel: float32 CUDA tensor [n] -> [n - 1]"""
+    torch = _torch()
+    x = x1d.reshape(1, -1).contiguous()
+    hx = hilbert_imag(x)
+    n = x.shape[1]
+    out = torch.empty(n - 1, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device.index):
+        _lib.check(_lib.lib().d4w_inst_freq(_lib.ptr(x, "float*"), _lib.ptr(hx, "float*"), n, float(fs), _lib.ptr(out, "float*"),
+                                            _lib.stream_ptr()), "inst_freq")
+    return out
 
 
 def snr(x, env=False):
@@ -283,18 +339,37 @@ def find_peaks_flags(x2d, prominence):
     return flags
 
 
+def compact_picks(flags):
+    """flags uint8 [rows, n] -> (offsets int32 [rows + 1], idx int32 [total]) on the device: ascending sample indices of
+    every row, rows concatenated (d4w_peaks_offsets / d4w_peaks_fill).  One 4-byte D2H read (the total) in between."""
+    torch = _torch()
+    rows_, n = flags.shape
+    L = _lib.lib()
+    counts = torch.empty(rows_, dtype=torch.int32, device=flags.device)
+    offsets = torch.empty(rows_ + 1, dtype=torch.int32, device=flags.device)
+    u8 = lambda t: _lib.ffi.cast("unsigned char*", t.data_ptr())
+    with torch.cuda.device(flags.device.index):
+        _lib.check(L.d4w_peaks_offsets(u8(flags), rows_, n, _lib.ptr(counts, "int*"), _lib.ptr(offsets, "int*"), _lib.stream_ptr()),
+                   "peaks_offsets")
+        total = int(offsets[-1].item())
+        idx = torch.empty(max(total, 1), dtype=torch.int32, device=flags.device)
+        if total:
+            _lib.check(L.d4w_peaks_fill(u8(flags), rows_, n, _lib.ptr(offsets, "int*"), _lib.ptr(idx, "int*"), _lib.stream_ptr()),
+                       "peaks_fill")
+    return offsets, idx[:total]
+
+
+def find_peaks_device(x2d, prominence):
+    """(offsets, idx) of compact_picks for scipy.signal.find_peaks(row, prominence=...) on every row; stays on the GPU."""
+    return compact_picks(find_peaks_flags(x2d, prominence))
+
+
 def find_peaks(x2d, prominence):
     """Per-row peak indices (list of int64 ndarrays, ascending) -- only the picks leave the GPU."""
-    import numpy as np
-    torch = _torch()
-    flags = find_peaks_flags(x2d, prominence)
-    nz = torch.nonzero(flags)                     # row-major order: rows ascending, indices ascending within a row
-    rows_ = x2d.shape[0]
-    if nz.numel() == 0:
-        return [np.empty(0, dtype=np.int64) for _ in range(rows_)]
-    nz = nz.cpu().numpy()
-    counts = np.bincount(nz[:, 0], minlength=rows_)
-    return np.split(nz[:, 1].astype(np.int64, copy=False), np.cumsum(counts)[:-1])
+    offsets, idx = find_peaks_device(x2d, prominence)
+    off = offsets.cpu().numpy().astype(np.int64)
+    ii = idx.cpu().numpy().astype(np.int64)
+    return [ii[off[r]:off[r + 1]] for r in range(x2d.shape[0])]
 
 
 def raw2strain(raw2d, scale_factor):

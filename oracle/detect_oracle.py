@@ -149,3 +149,27 @@ def compute_cross_correlogram_spectrocorr(data, fs, flims, kernel, win_size, ove
         s, _, _ = get_sliced_nspectrogram(data[i], fs, fmin, fmax, nperseg, nhop)
         out[i] = xcorr2d(s, ker)
     return out
+
+
+def process_corr(corr, threshold):
+    """detect.py:198-218"""
+    return sps.find_peaks(np.abs(sps.hilbert(corr)), prominence=threshold)[0]
+
+
+def nxcorr2d(spectro, kernel):
+    """detect.py:544-576"""
+    c = sps.correlate(spectro, kernel, mode="same", method="fft") / (np.std(spectro) * np.std(kernel) * spectro.shape[1])
+    return np.max(c, axis=0)
+
+
+def xcorr(t, f, Sxx, tvec, fvec, BlueKernel):
+    """detect.py:605-647 -- explicit sliding dot product"""
+    tsz, fsz = np.size(tvec), np.size(fvec)
+    cv = np.zeros(np.size(t) - (tsz - 1))
+    for i in range(np.size(t) - tsz + 1):
+        cv[i] = np.sum(BlueKernel * Sxx[:fsz, i:i + tsz])
+    cv /= (np.median(Sxx) * tsz)
+    cv[0] = 0
+    cv[-1] = 0
+    cv[cv < 0] = 0
+    return [t[int(tsz / 2) - 1:-int(np.ceil(tsz / 2))], cv]

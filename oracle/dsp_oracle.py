@@ -290,3 +290,17 @@ def snr_tr_array(trace, env=False):
     num = hilbert_envelope(trace) ** 2 if env else trace ** 2
     with np.errstate(divide="ignore"):
         return 10 * np.log10(num / var)
+
+
+def get_fx(trace, nfft):
+    """dsp.py:18-38 -- per-channel FFT magnitude, fftshift-ed, in nano-strain"""
+    fx = 2 * (abs(np.fft.fftshift(np.fft.fft(np.asarray(trace, dtype=np.float64), nfft), axes=1)))
+    fx /= nfft
+    fx *= 10 ** 9
+    return fx
+
+
+def instant_freq(channel, fs):
+    """dsp.py:830-856"""
+    import scipy.signal as sps
+    return np.diff(np.unwrap(np.angle(sps.hilbert(np.asarray(channel, dtype=np.float64))))) / (2.0 * np.pi) * fs

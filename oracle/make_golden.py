@@ -202,11 +202,94 @@ def main():
     rep["raw2strain"] = close(ref_strain, DH.raw2strain(raw, meta), what="raw2strain")
     np.savez_compressed(os.path.join(OUT, "raw2strain.npz"), raw=raw, scale_factor=meta["scale_factor"], strain=ref_strain)
 
+    rep.update(make_round2())
     for k, v in rep.items():
         print(f"{k:24s} oracle-vs-reference rel err {v:.2e}")
     tot = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))
     print(f"golden fixtures written to {OUT} ({tot / 1024:.0f} KiB)")
 
 
+def make_round2():
+    """Fixtures added in round 2: spectral views / alternate correlators (views.npz) and the Gabor image detector
+    (gabor.npz), again reference outputs with the oracle restatement asserted against them."""
+    import cv2
+    from oracle import improcess_oracle as IO
+    dsp, detect = ref_loader.load()
+    imp = ref_loader.load_improcess()
+    rep = {}
+    vw = {}
+    rng = np.random.default_rng(77)
+    # dsp.get_fx (dsp.py:18-38): crop (nfft < ns), exact (nfft == ns) and zero-pad (nfft > ns)
+    xfx = synth(5, 600, seed=31)
+    vw["fx_x"] = xfx
+    for nfft in (512, 600, 1000):
+        vw[f"fx_{nfft}"] = dsp.get_fx(xfx, nfft)
+        rep[f"get_fx_{nfft}"] = close(vw[f"fx_{nfft}"], O.get_fx(xfx, nfft), what="get_fx")
+    # dsp.instant_freq (dsp.py:830-856) on a chirp with a smooth envelope
+    tt = np.arange(1200) / FS
+    import scipy.signal as sps
+    ch = sps.chirp(tt, f0=12.0, f1=30.0, t1=tt[-1], method="linear") * (1.0 + 0.3 * np.sin(2 * np.pi * 0.7 * tt))
+    vw["if_x"] = ch
+    vw["if_y"] = dsp.instant_freq(ch, FS)
+    rep["instant_freq"] = close(vw["if_y"], O.instant_freq(ch, FS), what="instant_freq")
+    # detect.shift_xcorr / shift_nxcorr with unequal lengths (detect.py:96-137)
+    a = rng.standard_normal(300); b = rng.standard_normal(120); c = rng.standard_normal(420)
+    vw.update(sx_a=a, sx_b=b, sx_c=c, sx_ab=detect.shift_xcorr(a, b), sx_ac=detect.shift_xcorr(a, c),
+              snx_ab=detect.shift_nxcorr(a, b), snx_ac=detect.shift_nxcorr(a, c))
+    close(vw["sx_ab"], D.shift_xcorr(a, b)); close(vw["sx_ac"], D.shift_xcorr(a, c))
+    # detect.xcorr (detect.py:605-647), nxcorr2d (:544-576), process_corr (:198-218)
+    ff = np.linspace(0, FS / 2, 81)[12:32]
+    tgrid = np.linspace(0, 8.0, 201)
+    tv, fv, ker = detect.buildkernel(27., 16., 4., 0.9, ff, tgrid, FS, 12., 36.)
+    S = np.abs(rng.standard_normal((len(ff) + 5, 201)))
+    t_scale, cv = detect.xcorr(tgrid, ff, S, tv, fv, ker)
+    to, co = D.xcorr(tgrid, ff, S, tv, fv, ker)
+    rep["xcorr"] = close(cv, co, what="detect.xcorr"); close(t_scale, to, what="detect.xcorr t_scale")
+    nx2 = detect.nxcorr2d(S[:len(ff)], ker)
+    rep["nxcorr2d"] = close(nx2, D.nxcorr2d(S[:len(ff)], ker), what="nxcorr2d")
+    corr1 = synth(1, 1600, seed=41)[0] * 0.1
+    pc = detect.process_corr(corr1, 0.05)
+    assert np.array_equal(pc, D.process_corr(corr1, 0.05))
+    vw.update(xc_t=tgrid, xc_f=ff, xc_S=S, xc_tvec=tv, xc_fvec=fv, xc_ker=ker, xc_tscale=t_scale, xc_val=cv, nxc2d=nx2,
+              pc_x=corr1, pc_idx=pc)
+    np.savez_compressed(os.path.join(OUT, "views.npz"), **vw)
+
+    # ---- Gabor image detector (a15): improcess.py:44-63, :98-140, :395-454; scripts/main_gabordetect.py:78-169 ----------
+    gb = {}
+    nx, ns, sel = 400, 3000, [0, 400, 1]
+    trf = synth(nx, ns, seed=5, ncalls=4)
+    image = imp.trace2image(trf)
+    rep["trace2image"] = close(image, IO.trace2image(trf), what="trace2image")
+    theta = imp.angle_fromspeed(1500., FS, DX, sel)
+    imagebin = imp.binning(image, 1 / 10, 1 / 10)
+    rep["binning"] = close(imagebin, IO.binning(image, 1 / 10, 1 / 10), what="binning")
+    up, down = imp.gabor_filt_design(theta, plot=False)
+    uo, do = IO.gabor_filt_design(theta)
+    close(up, uo, what="gabor up"); close(down, do, what="gabor down")
+    fimage = cv2.filter2D(imagebin, cv2.CV_64F, up) + cv2.filter2D(imagebin, cv2.CV_64F, down)     # main_gabordetect.py:109
+    thr = float(np.percentile(fimage, 90.0))
+    binary = fimage > thr
+    m2 = cv2.filter2D(binary.astype(float), cv2.CV_64F, up) + cv2.filter2D(binary.astype(float), cv2.CV_64F, down)   # :135
+    thr2 = float(np.percentile(m2, 85.0))
+    mask = m2 > thr2
+    smoothed = imp.apply_smooth_mask(imagebin, mask)
+    mask_sparse = imp.binning(mask, 10, 10)                                                          # :166
+    masked = imp.apply_smooth_mask(trf, mask_sparse)                                                 # :169
+    mo, parts = IO.gabor_detect(trf, FS, DX, sel, 1500., 10, thr, thr2)
+    rep["gabor_fimage"] = close(fimage, parts["fimage"], what="gabor fimage")
+    assert np.array_equal(mask, parts["mask"]) and np.array_equal(mask_sparse, parts["mask_sparse"])
+    rep["gabor_masked"] = close(masked, mo, what="gabor masked trace")
+    rows = np.array([0, 57, 133, 200, 311, 399])
+    gb.update(seed=5, nx=nx, ns=ns, ncalls=4, x_checksum=float(np.sum(trf)), theta=theta, up=up, image_rows=image[rows], rows=rows,
+              imagebin=imagebin, fimage=fimage, thr=thr, m2=m2, thr2=thr2, mask=mask, smoothed=smoothed,
+              mask_sparse_bits=np.packbits(mask_sparse), masked_rows=masked[rows])
+    np.savez_compressed(os.path.join(OUT, "gabor.npz"), **gb)
+    return rep
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "round2":
+        for k, v in make_round2().items():
+            print(f"{k:24s} oracle-vs-reference rel err {v:.2e}")
+    else:
+        main()

@@ -99,3 +99,27 @@ def load_data_handle():
     spec.loader.exec_module(m)
     _cache["dh"] = m
     return m
+
+
+def load_improcess():
+    """The reference's improcess module (unmodified).  Its real dependencies cv2 / torch / torchvision are importable here;
+    skimage and matplotlib are stubbed (only used by functions outside the Gabor path)."""
+    if "imp" in _cache:
+        return _cache["imp"]
+    load()
+    for n in ("skimage", "skimage.transform"):
+        try:
+            importlib.import_module(n)
+        except Exception:
+            _stub(n)
+    st = sys.modules["skimage.transform"]
+    for name in ("radon", "iradon"):
+        if not hasattr(st, name):
+            setattr(st, name, lambda *a, **k: None)
+    sys.modules["skimage"].transform = st
+    spec = importlib.util.spec_from_file_location("das4whales.improcess", os.path.join(_SRC, "improcess.py"))
+    m = importlib.util.module_from_spec(spec)
+    sys.modules[spec.name] = m
+    spec.loader.exec_module(m)
+    _cache["imp"] = m
+    return m

@@ -52,3 +52,11 @@ def test_sass_is_sm100a(libpath):
     out = subprocess.run([exe, "--list-elf", libpath], capture_output=True, text=True).stdout
     assert "sm_100a" in out
     assert all("sm_100a" in line for line in out.splitlines() if "ELF file" in line)
+
+
+def test_packaged_header_matches_canonical(libpath):
+    """das4whales_b200/d4w.h (shipped with the package) must be byte-identical to include/d4w.h."""
+    root = os.path.join(os.path.dirname(_lib.HERE), "include", "d4w.h")
+    pkg = os.path.join(_lib.HERE, "d4w.h")
+    assert os.path.exists(root) and os.path.exists(pkg)
+    assert open(root, "rb").read() == open(pkg, "rb").read()

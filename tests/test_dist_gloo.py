@@ -28,11 +28,11 @@ class NumpyBackend:
     def empty(self, shape, complex_=False):
         return torch.zeros(shape, dtype=torch.complex128 if complex_ else torch.float64)
 
-    def col_fwd(self, xs, w_slab, taper, t_offset):
+    def col_fwd(self, xs, taper, t_offset):
         x = xs.numpy()
         if taper:
             x = x * self.taper[t_offset:t_offset + x.shape[1]][None, :]
-        w_slab[: self.rows] = torch.from_numpy(np.fft.fft(x, axis=0)[self.act])
+        return torch.from_numpy(np.fft.fft(x, axis=0)[self.act])
 
     def row_filter(self, w_rows, slot_begin, count):
         if count:
@@ -40,8 +40,13 @@ class NumpyBackend:
             f = np.fft.fft(w_rows[:count].numpy(), axis=1) * self.msym[ks]
             w_rows[:count] = torch.from_numpy(np.fft.ifft(f, axis=1))
 
-    def col_inv(self, w_slab, ys):
-        w = w_slab.numpy()
+    def col_inv_input(self):
+        if getattr(self, "_w", None) is None:
+            self._w = torch.zeros((self.rows, self.ns // self.world), dtype=torch.complex128)
+        return self._w
+
+    def col_inv(self, ys):
+        w = self._w.numpy()
         spec = np.zeros((self.nx, w.shape[1]), dtype=np.complex128)
         for s, k in enumerate(self.act):
             spec[k] = w[s]
@@ -86,10 +91,29 @@ def test_sharded_fk_world2_gloo(nx, ns, taper):
         assert rows_per * 2 >= rows > 0
 
 
+@pytest.mark.parametrize("nx,ns,world", [(24, 160, 2), (36, 96, 3), (32, 64, 4)])
+def test_local_group_driver_matches_oracle(nx, ns, world):
+    """dist.run_local_group (the in-process stand-in for the collectives, used by the single-GPU test of the CUDA
+    backend) against the float64 oracle, uneven row splits included."""
+    sys.path.insert(0, ROOT)
+    from das4whales_b200 import dist as d4wdist
+    from oracle import dsp_oracle as O
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal((nx, ns))
+    mask = O.fk_filter_design((nx, ns), [0, nx, 1], DX, FS)
+    cpr = nx // world
+    filters = [d4wdist.ShardedFkFilter(nx, ns, NumpyBackend(mask, nx, ns, world), rank=r, world=world) for r in range(world)]
+    ys = d4wdist.run_local_group(filters, [torch.from_numpy(x[r * cpr:(r + 1) * cpr].copy()) for r in range(world)], tapering=True)
+    ref = O.fk_filter_filt(x.copy(), mask, tapering=True)
+    got = np.concatenate([y.numpy() for y in ys], axis=0)
+    assert np.max(np.abs(got - ref)) / np.max(np.abs(ref)) <= 1e-12
+
+
 def test_partition_rules():
     sys.path.insert(0, ROOT)
     from das4whales_b200.dist import partition
     p = partition(20000, 240000, 2711, 4)
-    assert p == {"cpr": 5000, "slab": 60000, "rows_per": 678, "rows_pad": 2712}
+    assert p == {"cpr": 5000, "slab": 60000, "rows_per": 678, "counts": [678, 678, 678, 677]}
+    assert partition(8, 16, 3, 4)["counts"] == [1, 1, 1, 0]
     with pytest.raises(ValueError):
         partition(10001, 120000, 100, 2)
