@@ -114,6 +114,16 @@ extern "C" int d4w_xcorr(d4w_fft_plan* p, const float* x, int nx, int ns, int va
     xp.pl = p->pl; xp.tw = p->d_tw; xp.nb = p->n; xp.valid = valid; xp.ntpl = ntpl; xp.ns = ns;
     xp.normalize = normalize ? 1 : 0;
     xp.nseg = (ns + valid - 1) / valid;
+    // dual-lane kernel (four segments per CTA, packed f32x2 butterflies): needs the fused plan shape; 2 CTAs per SM
+    const size_t smem_dual = (size_t)2 * p->n * 16 + (size_t)((valid + 7) / 8) * 16 + (size_t)valid * 8 + 16;
+    if (p->fused && p->pl.nstages >= 2 && smem_dual <= 110 * 1024 && env_int("D4W_XCORR_DUAL", 1)) {
+        D4W_CUDA_TRY(cudaFuncSetAttribute(k_xcorr_dual, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+        dim3 gridd((xp.nseg + 3) / 4, nx);
+        k_xcorr_dual<<<gridd, 128, smem_dual, (cudaStream_t)stream>>>(xp, x, (const float2*)dev_tabs, dev_stats, dev_segpre, dev_mu_over_m,
+                                                                     out, (size_t)nx * ns);
+        D4W_CHECK_LAUNCH("k_xcorr_dual");
+        return D4W_OK;
+    }
     const size_t smem = (size_t)3 * p->n * sizeof(float2);
     if (smem + 1024 > p->smem_cap) return fail(D4W_ERR_UNSUPPORTED, "d4w_xcorr: block length too large for shared memory");
     dim3 grid((xp.nseg + 1) / 2, nx);

@@ -7,6 +7,7 @@
 //   dsp.bp_filt (scipy filtfilt) and caller-side sosfiltfilt dsp.py:859-880, Example.py:55
 //   dsp.get_spectrogram / detect.get_sliced_nspectrogram     dsp.py:41-78, detect.py:334-408
 #pragma once
+#include <cuda_fp16.h>
 #include <type_traits>
 #include "fft_smem.cuh"
 #include "fk_kernels.cuh"
@@ -266,6 +267,148 @@ k_xcorr_fused(XcorrParams xp, const float* __restrict__ x, const float2* __restr
         const float mu = xp.normalize ? (float)mu_over_m[t] : 0.f;
         float* o = out + (size_t)t * out_tpl_stride + (size_t)row * ns;
 #define D4W_CALL(R) xcorr_first_inv_out<R>(B, P, xp.tw, nb, V, ta, tb, ns, mu, xp.normalize != 0, o, tid, nthr);
+        D4W_ROW_RADIX_SWITCH(r0, D4W_CALL)
+#undef D4W_CALL
+        __syncthreads();
+    }
+}
+
+// ---- dual-lane variant: FOUR consecutive segments of one channel per CTA as the two f32x2 lanes of the dual engine ---------
+// Element i of the block is the 16-byte cpd {x = (seg_a[i], seg_c[i]), y = (seg_b[i], seg_d[i])}: lane A is the complex
+// signal a + i b, lane B is c + i d, and both lanes run through one instruction stream of packed FFMA2 / FADD2 / FMUL2
+// butterflies (the scalar kernel saturates the FMA pipe at 50 % issue: 3-register FFMA issues every other cycle per SMSP).
+// The template spectra are lane-independent scalars (dmul_s).  Shared memory: S and B as cpd (16 B x nb each) and the
+// exclusive prefix sums of the mu term as a coarse float4 per 8 samples + an fp16 x 4 remainder per sample (the remainder is
+// a sum of <= 7 normalised samples, |.| <= 7, so its fp16 rounding is <= 4e-3 before the ~1e-6 factor mu / m).
+struct __align__(8) half4 { __half2 ac, bd; };
+
+template <int R>
+__device__ __forceinline__ void xcorrd_last_fused(const cpd* __restrict__ S, cpd* __restrict__ B, const float2* __restrict__ tab,
+                                                  int nb, int tid, int nthr) {
+    const int G = nb / R;
+    for (int j = tid; j < G; j += nthr) {
+        cpd v[R], u[R];
+        static_for<R>([&](auto qc) { constexpr int q = decltype(qc)::value; v[q] = S[j * R + q]; });
+        DFTD<R, false>::run(v);                                                  // X[m] at v[outpos(m)]
+        static_for<R>([&](auto mc) { constexpr int m = decltype(mc)::value; u[m] = dmul_s(v[outpos<R>(m)], tab[m * G + j]); });
+        DFTD<R, true>::run(u);
+        static_for<R>([&](auto qc) { constexpr int q = decltype(qc)::value; B[j * R + q] = u[outpos<R>(q)]; });
+    }
+}
+template <int R>
+__device__ __forceinline__ void xcorrd_first_inv_out(const cpd* __restrict__ B, const float4* __restrict__ Pc, const half4* __restrict__ Pf,
+                                                     const float2* __restrict__ tw, int nb, int V, int t0, int ns, float mu, bool use_p,
+                                                     float* __restrict__ o, int tid, int nthr) {
+    const int L = nb / R;
+    for (int n = tid; n < L; n += nthr) {
+        cpd v[R];
+        static_for<R>([&](auto mc) { constexpr int m = decltype(mc)::value; v[m] = B[n + m * L]; });
+        if (L > 1) apply_stage_twiddles<R, true, false>(v, tw[n]);
+        DFTD<R, true>::run(v);
+        static_for<R>([&](auto qc) {
+            constexpr int q = decltype(qc)::value;
+            const int i = n + q * L;
+            if (i < V) {
+                const cpd z = v[outpos<R>(q)];
+                float va = f2x_lo(z.x), vc = f2x_hi(z.x), vb = f2x_lo(z.y), vd = f2x_hi(z.y);
+                if (use_p) {
+                    const float4 c = Pc[i >> 3];
+                    const half4 f = Pf[i];
+                    const float2 fac = __half22float2(f.ac), fbd = __half22float2(f.bd);
+                    va += mu * (c.x + fac.x); vb += mu * (c.y + fbd.x); vc += mu * (c.z + fac.y); vd += mu * (c.w + fbd.y);
+                }
+                const int ta = t0 + i, tb = ta + V, tc = tb + V, td = tc + V;
+                if (ta < ns) o[ta] = va;
+                if (tb < ns) o[tb] = vb;
+                if (tc < ns) o[tc] = vc;
+                if (td < ns) o[td] = vd;
+            }
+        });
+    }
+}
+
+static __global__ void __launch_bounds__(128, 2)
+k_xcorr_dual(XcorrParams xp, const float* __restrict__ x, const float2* __restrict__ tabs, const double* __restrict__ stats,
+             const double* __restrict__ segpre, const double* __restrict__ mu_over_m, float* __restrict__ out, size_t out_tpl_stride) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    const int ns = xp.ns, nb = xp.nb, V = xp.valid, nst = xp.pl.nstages;
+    const int ng = (V + 7) >> 3;                           // prefix groups of 8 samples
+    cpd* S = reinterpret_cast<cpd*>(smraw);
+    cpd* B = S + nb;
+    float4* Pc = reinterpret_cast<float4*>(B + nb);
+    half4* Pf = reinterpret_cast<half4*>(Pc + ng);
+    __shared__ float4 s_wsum[8];
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, wid = tid >> 5;
+    const int row = blockIdx.y;
+    const int seg0 = 4 * blockIdx.x;
+    const int t0 = seg0 * V;
+    const float* r = x + (size_t)row * ns;
+    float mean = 0.f, inv = 1.f;
+    if (xp.normalize) { mean = (float)stats[4 * (size_t)row]; inv = (float)(1.0 / stats[4 * (size_t)row + 1]); }
+    for (int i = tid; i < nb; i += nthr) {
+        const int ia = t0 + i, ib = ia + V, ic = ib + V, id = ic + V;
+        const float a = (ia < ns) ? (r[ia] - mean) * inv : 0.f;
+        const float b = (ib < ns) ? (r[ib] - mean) * inv : 0.f;
+        const float c = (ic < ns) ? (r[ic] - mean) * inv : 0.f;
+        const float d = (id < ns) ? (r[id] - mean) * inv : 0.f;
+        S[i] = dmake(f2x_set(a, c), f2x_set(b, d));
+    }
+    __syncthreads();
+    if (xp.normalize) {
+        // exclusive prefix of the first V samples of each of the four segments: thread -> contiguous run of groups
+        const int gpt = (ng + nthr - 1) / nthr;
+        const int g0 = min(ng, tid * gpt), g1 = min(ng, g0 + gpt);
+        float4 loc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = g0 * 8; i < min(V, g1 * 8); ++i) {
+            const cpd z = S[i];
+            loc.x += f2x_lo(z.x); loc.y += f2x_lo(z.y); loc.z += f2x_hi(z.x); loc.w += f2x_hi(z.y);
+        }
+        float4 inc = loc;
+        for (int o = 1; o < 32; o <<= 1) {
+            const float ux = __shfl_up_sync(0xffffffffu, inc.x, o), uy = __shfl_up_sync(0xffffffffu, inc.y, o);
+            const float uz = __shfl_up_sync(0xffffffffu, inc.z, o), uw = __shfl_up_sync(0xffffffffu, inc.w, o);
+            if (lane >= o) { inc.x += ux; inc.y += uy; inc.z += uz; inc.w += uw; }
+        }
+        if (lane == 31) s_wsum[wid] = inc;
+        __syncthreads();
+        float4 run = make_float4(inc.x - loc.x, inc.y - loc.y, inc.z - loc.z, inc.w - loc.w);
+        for (int w = 0; w < wid; ++w) { run.x += s_wsum[w].x; run.y += s_wsum[w].y; run.z += s_wsum[w].z; run.w += s_wsum[w].w; }
+        const size_t sp = (size_t)row * xp.nseg + seg0;
+        run.x += (seg0 + 0 < xp.nseg) ? (float)segpre[sp + 0] : 0.f;
+        run.y += (seg0 + 1 < xp.nseg) ? (float)segpre[sp + 1] : 0.f;
+        run.z += (seg0 + 2 < xp.nseg) ? (float)segpre[sp + 2] : 0.f;
+        run.w += (seg0 + 3 < xp.nseg) ? (float)segpre[sp + 3] : 0.f;
+        for (int g = g0; g < g1; ++g) {
+            Pc[g] = run;
+            float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = g * 8; i < min(V, g * 8 + 8); ++i) {
+                half4 h; h.ac = __floats2half2_rn(f.x, f.z); h.bd = __floats2half2_rn(f.y, f.w);
+                Pf[i] = h;
+                const cpd z = S[i];
+                f.x += f2x_lo(z.x); f.y += f2x_lo(z.y); f.z += f2x_hi(z.x); f.w += f2x_hi(z.y);
+            }
+            run.x += f.x; run.y += f.y; run.z += f.z; run.w += f.w;
+        }
+        __syncthreads();
+    }
+    for (int st = 0; st < nst - 1; ++st) {
+        stage_dispatch_dual<false>(S, xp.tw, nb, xp.pl.sub[st], xp.pl.radix[st], 1, nb, tid, nthr);
+        __syncthreads();
+    }
+    const int r0 = xp.pl.radix[0], rl = xp.pl.radix[nst - 1];
+    for (int t = 0; t < xp.ntpl; ++t) {
+        const float2* tab = tabs + (size_t)t * nb;
+#define D4W_CALL(R) xcorrd_last_fused<R>(S, B, tab, nb, tid, nthr);
+        D4W_ROW_RADIX_SWITCH(rl, D4W_CALL)
+#undef D4W_CALL
+        __syncthreads();
+        for (int st = nst - 2; st >= 1; --st) {
+            stage_dispatch_dual<true>(B, xp.tw, nb, xp.pl.sub[st], xp.pl.radix[st], 1, nb, tid, nthr);
+            __syncthreads();
+        }
+        const float mu = xp.normalize ? (float)mu_over_m[t] : 0.f;
+        float* o = out + (size_t)t * out_tpl_stride + (size_t)row * ns;
+#define D4W_CALL(R) xcorrd_first_inv_out<R>(B, Pc, Pf, xp.tw, nb, V, t0, ns, mu, xp.normalize != 0, o, tid, nthr);
         D4W_ROW_RADIX_SWITCH(r0, D4W_CALL)
 #undef D4W_CALL
         __syncthreads();

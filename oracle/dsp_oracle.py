@@ -199,15 +199,24 @@ def taper_data(trace):
     return trace
 
 
-def fk_filter_filt(trace, fk_filter_matrix, tapering=False):
+def fk_filter_filt(trace, fk_filter_matrix, tapering=False, workers=None):
     """fft2 -> shift -> x mask -> unshift -> ifft2 -> real  -- dsp.py:725-756.
-    (fk_filter_sparsefilt, :759-786, is the same arithmetic with a COO mask.)"""
+    (fk_filter_sparsefilt, :759-786, is the same arithmetic with a COO mask.)
+
+    workers=None: numpy.fft, single-threaded, exactly the reference's calls.  workers=N: the same statements with
+    scipy.fft (the same pocketfft algorithm, N threads) -- bench.py's all-host-cores CPU arm; pinned equal to the
+    numpy.fft route by tests/test_oracle_golden.py."""
     trace = np.asarray(trace, dtype=np.float64)
     if tapering:
         trace = taper_data(trace)
-    spec = np.fft.fftshift(np.fft.fft2(trace))
-    spec = spec * np.asarray(fk_filter_matrix)
-    return np.fft.ifft2(np.fft.ifftshift(spec)).real
+    if workers is None:
+        spec = np.fft.fftshift(np.fft.fft2(trace))
+        spec = spec * np.asarray(fk_filter_matrix)
+        return np.fft.ifft2(np.fft.ifftshift(spec)).real
+    import scipy.fft as sfft
+    spec = sfft.fftshift(sfft.fft2(trace, workers=workers))
+    spec *= np.asarray(fk_filter_matrix)
+    return sfft.ifft2(sfft.ifftshift(spec), workers=workers, overwrite_x=True).real
 
 
 def fk_filter_filt_rows(trace, fk_filter_matrix, rows, cols=None, tapering=False):

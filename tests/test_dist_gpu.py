@@ -59,8 +59,8 @@ def test_sharded_cuda_backend_local_group(dw, nx, ns, world, kind, taper):
     if nx * ns <= 5_000_000:
         from oracle import dsp_oracle as O
         xo = x.cpu().numpy().astype(np.float64)
-        mo = O.fk_filter_design((nx, ns), [0, nx, 1], DX, FS) if kind == "fan" else \\
-            O.hybrid_ninf_filter_design((nx, ns), [0, nx, 1], DX, FS, 1350., 1450., 3300, 3450, 14., 30.)
+        mo = (O.fk_filter_design((nx, ns), [0, nx, 1], DX, FS) if kind == "fan" else
+              O.hybrid_ninf_filter_design((nx, ns), [0, nx, 1], DX, FS, 1350., 1450., 3300, 3450, 14., 30.))
         eo = rel_err(got.cpu().numpy(), O.fk_filter_filt(xo, mo, tapering=taper))
         assert eo[0] <= 2e-5, eo
 

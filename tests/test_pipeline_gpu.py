@@ -1,0 +1,60 @@
+"""GPU test of the file-level detection pipeline (BASELINE config 5 path, das4whales_b200/pipeline.py) against the float64
+oracle chain that restates scripts/main_mfdetect.py:42-103: raw2strain -> bp_filt -> hybrid_ninf f-k filter -> HF / LF
+cross-correlograms -> threshold 0.5 * max -> pick_times_env."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+DX, FS = 2.0419046878814697, 200.0
+
+
+@pytest.fixture(scope="module")
+def dw():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import das4whales_b200 as dw
+    from das4whales_b200 import _lib
+    _lib.lib()
+    return dw
+
+
+def _oracle_chain(raw, scale, sel):
+    from oracle import dsp_oracle as O, detect_oracle as D, data_oracle as DH
+    nx, ns = raw.shape
+    x = DH.raw2strain(raw, {"scale_factor": scale})
+    x = O.bp_filt(x, FS, 14., 30.)
+    m = O.hybrid_ninf_filter_design((nx, ns), sel, DX, FS, 1350., 1450., 3300, 3450, 14., 30.)
+    y = O.fk_filter_filt(x, m)
+    t = np.arange(ns) / FS
+    hf = D.gen_template_fincall(t, FS, 17.8, 28.8, 0.68)
+    lf = D.gen_template_fincall(t, FS, 14.7, 21.8, 0.78)
+    chf, clf = D.compute_cross_correlogram(y, hf), D.compute_cross_correlogram(y, lf)
+    maxv = max(chf.max(), clf.max())
+    thr = 0.5 * maxv
+    return maxv, D.convert_pick_times(D.pick_times_env(chf, thr * 0.9)), D.convert_pick_times(D.pick_times_env(clf, thr)), chf, thr
+
+
+def test_mfdetect_pipeline_matches_oracle_chain(dw):
+    from das4whales_b200 import pipeline
+    from oracle.make_golden import synth
+    nx, ns, sel = 240, 6000, [0, 240, 1]
+    x = synth(nx, ns, seed=9, ncalls=3)
+    counts = np.round(x * 5.0e4).astype(np.int32) + 1234          # interrogator counts with an offset
+    scale = 4.0838e-11 * 1550.0 / 2.0419
+    pipe = pipeline.MfDetectPipeline(nx, ns, sel, DX, FS, scale)
+    res = pipe.process_file(counts)
+    maxv, phf, plf, chf, thr = _oracle_chain(counts, scale, sel)
+    assert abs(res["maxv"] - maxv) <= 1e-4 * maxv
+    for got, ref in ((res["picks_hf"], phf), (res["picks_lf"], plf)):
+        a = set(zip(got[0].tolist(), got[1].tolist()))
+        b = set(zip(ref[0].tolist(), ref[1].tolist()))
+        # picks whose prominence sits within fp32 rounding of the threshold may differ; everything else must agree
+        assert len(a ^ b) <= max(2, len(b) // 100), (len(a), len(b), len(a ^ b))
+        assert len(b) > 0
+    # streaming three files gives the same answer for each (double-buffered uploads)
+    outs = list(pipe.stream([counts, counts.astype(np.float32), counts]))
+    for o in outs:
+        assert np.array_equal(o["picks_hf"], res["picks_hf"]) and np.array_equal(o["picks_lf"], res["picks_lf"])
+    one = pipeline.process_file(counts, {"dx": DX, "fs": FS, "scale_factor": scale}, sel)
+    assert np.array_equal(one["picks_hf"], res["picks_hf"])
