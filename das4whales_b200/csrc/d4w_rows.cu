@@ -32,7 +32,10 @@ extern "C" int d4w_fft_plan_create(d4w_fft_plan** out, int n, int device) {
     std::string err;
     // overlap-save block lengths (rows.py _pick_block): big even radix first, small odd radix last suits k_xcorr_fused
     const char* forced = std::getenv("D4W_BLOCK_PLAN");
-    const char* pref = n == 1250 ? "10,25,5" : n == 2500 ? "20,25,5" : n == 5000 ? "20,10,25" : n == 10000 ? "20,20,25" : nullptr;
+    // dual-lane matched filter (default): radices <= 10 only (register budget of two 256-thread CTAs per SM)
+    const bool dual_blocks = env_int("D4W_XCORR_DUAL", 1) != 0;
+    const char* pref = dual_blocks ? (n == 1250 ? "10,5,5,5" : n == 2500 ? "10,10,5,5" : n == 5000 ? "10,10,10,5" : n == 10000 ? "10,10,10,10" : nullptr)
+                                   : (n == 1250 ? "10,25,5" : n == 2500 ? "20,25,5" : n == 5000 ? "20,10,25" : n == 10000 ? "20,20,25" : nullptr);
     bool have = false;
     if (forced && *forced) have = make_plan_from_string(n, forced, p->pl);
     if (!have && pref && env_int("D4W_XCORR_FUSED", 1)) have = make_plan_from_string(n, pref, p->pl);
@@ -116,10 +119,12 @@ extern "C" int d4w_xcorr(d4w_fft_plan* p, const float* x, int nx, int ns, int va
     xp.nseg = (ns + valid - 1) / valid;
     // dual-lane kernel (four segments per CTA, packed f32x2 butterflies): needs the fused plan shape; 2 CTAs per SM
     const size_t smem_dual = (size_t)2 * p->n * 16 + (size_t)((valid + 7) / 8) * 16 + (size_t)valid * 8 + 16;
-    if (p->fused && p->pl.nstages >= 2 && smem_dual <= 110 * 1024 && env_int("D4W_XCORR_DUAL", 1)) {
+    bool small_radices = true;
+    for (int st = 0; st < p->pl.nstages; ++st) small_radices = small_radices && xcorr_dual_radix_ok(p->pl.radix[st]);
+    if (p->fused && p->pl.nstages >= 2 && small_radices && smem_dual <= 110 * 1024 && env_int("D4W_XCORR_DUAL", 1)) {
         D4W_CUDA_TRY(cudaFuncSetAttribute(k_xcorr_dual, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
         dim3 gridd((xp.nseg + 3) / 4, nx);
-        k_xcorr_dual<<<gridd, 128, smem_dual, (cudaStream_t)stream>>>(xp, x, (const float2*)dev_tabs, dev_stats, dev_segpre, dev_mu_over_m,
+        k_xcorr_dual<<<gridd, 256, smem_dual, (cudaStream_t)stream>>>(xp, x, (const float2*)dev_tabs, dev_stats, dev_segpre, dev_mu_over_m,
                                                                      out, (size_t)nx * ns);
         D4W_CHECK_LAUNCH("k_xcorr_dual");
         return D4W_OK;
@@ -302,11 +307,30 @@ extern "C" int d4w_sosfiltfilt(const float* x, float* y, float* tmp, int nx, int
         if (next < 2 * chunk) chunk = 0;          // short signals: plain sequential recursion
     }
     const int nchunks = chunk > 0 ? (next + chunk - 1) / chunk : 1;
-    dim3 grid(blocks, nchunks);
-    k_sos_pass<1><<<grid, 32, 0, stream>>>(sp, x, tmp, y, nx, chunk, warm);
-    D4W_CHECK_LAUNCH("k_sos_pass<fwd>");
-    k_sos_pass<-1><<<grid, 32, 0, stream>>>(sp, x, tmp, y, nx, chunk, warm);
-    D4W_CHECK_LAUNCH("k_sos_pass<bwd>");
+    // four warps per block (one 32-channel group each); with time chunking every warp walks two chunks at once
+    const int nch = (nchunks >= 2 && env_int("D4W_IIR_NCH", 2) >= 2) ? 2 : 1;
+    dim3 grid((blocks + 3) / 4, (nchunks + nch - 1) / nch);
+#define D4W_SOS(NS_, NCH_)                                                                               \
+    do {                                                                                                 \
+        k_sos_pass<1, NS_, NCH_><<<grid, 128, 0, stream>>>(sp, x, tmp, y, nx, chunk, warm, nchunks);     \
+        D4W_CHECK_LAUNCH("k_sos_pass<fwd>");                                                             \
+        k_sos_pass<-1, NS_, NCH_><<<grid, 128, 0, stream>>>(sp, x, tmp, y, nx, chunk, warm, nchunks);    \
+        D4W_CHECK_LAUNCH("k_sos_pass<bwd>");                                                             \
+    } while (0)
+    if (nch == 2) {
+        switch (nsec) {
+            case 1: D4W_SOS(1, 2); break; case 2: D4W_SOS(2, 2); break; case 3: D4W_SOS(3, 2); break; case 4: D4W_SOS(4, 2); break;
+            case 5: D4W_SOS(5, 2); break; case 6: D4W_SOS(6, 2); break; case 8: D4W_SOS(8, 2); break;
+            default: D4W_SOS(0, 1); break;
+        }
+    } else {
+        switch (nsec) {
+            case 1: D4W_SOS(1, 1); break; case 2: D4W_SOS(2, 1); break; case 3: D4W_SOS(3, 1); break; case 4: D4W_SOS(4, 1); break;
+            case 5: D4W_SOS(5, 1); break; case 6: D4W_SOS(6, 1); break; case 8: D4W_SOS(8, 1); break;
+            default: D4W_SOS(0, 1); break;
+        }
+    }
+#undef D4W_SOS
     return D4W_OK;
 }
 

@@ -327,7 +327,23 @@ __device__ __forceinline__ void xcorrd_first_inv_out(const cpd* __restrict__ B, 
     }
 }
 
-static __global__ void __launch_bounds__(128, 2)
+// Small-radix dispatch: the dual kernel is compiled for radices <= 10 only, so that its register allocation (the maximum
+// over every path in the kernel) stays <= 128 and two 256-thread CTAs share an SM (16 warps); blocks are planned as
+// 10 . 10 . 5 . 5 (2500) etc.: 250 - 500 butterflies per stage keep all 256 threads busy.
+#define D4W_SMALL_RADIX_SWITCH(r, CALL)                                                                       \
+    switch (r) {                                                                                              \
+        case 2: { CALL(2) } break; case 3: { CALL(3) } break; case 4: { CALL(4) } break; case 5: { CALL(5) } break;         \
+        case 6: { CALL(6) } break; case 8: { CALL(8) } break; default: { CALL(10) } break;                                   \
+    }
+__host__ __device__ inline bool xcorr_dual_radix_ok(int r) { return r == 2 || r == 3 || r == 4 || r == 5 || r == 6 || r == 8 || r == 10; }
+template <bool INV>
+__device__ __forceinline__ void stage_dispatch_dual_small(cpd* s, const float2* tw, int n_total, int ns, int r, int tid, int nthr) {
+#define D4W_CALL(R) stage_dual<R, INV>(s, tw, n_total, ns, 1, n_total, tid, nthr);
+    D4W_SMALL_RADIX_SWITCH(r, D4W_CALL)
+#undef D4W_CALL
+}
+
+static __global__ void __launch_bounds__(256, 2)
 k_xcorr_dual(XcorrParams xp, const float* __restrict__ x, const float2* __restrict__ tabs, const double* __restrict__ stats,
              const double* __restrict__ segpre, const double* __restrict__ mu_over_m, float* __restrict__ out, size_t out_tpl_stride) {
     extern __shared__ __align__(16) unsigned char smraw[];
@@ -392,24 +408,24 @@ k_xcorr_dual(XcorrParams xp, const float* __restrict__ x, const float2* __restri
         __syncthreads();
     }
     for (int st = 0; st < nst - 1; ++st) {
-        stage_dispatch_dual<false>(S, xp.tw, nb, xp.pl.sub[st], xp.pl.radix[st], 1, nb, tid, nthr);
+        stage_dispatch_dual_small<false>(S, xp.tw, nb, xp.pl.sub[st], xp.pl.radix[st], tid, nthr);
         __syncthreads();
     }
     const int r0 = xp.pl.radix[0], rl = xp.pl.radix[nst - 1];
     for (int t = 0; t < xp.ntpl; ++t) {
         const float2* tab = tabs + (size_t)t * nb;
 #define D4W_CALL(R) xcorrd_last_fused<R>(S, B, tab, nb, tid, nthr);
-        D4W_ROW_RADIX_SWITCH(rl, D4W_CALL)
+        D4W_SMALL_RADIX_SWITCH(rl, D4W_CALL)
 #undef D4W_CALL
         __syncthreads();
         for (int st = nst - 2; st >= 1; --st) {
-            stage_dispatch_dual<true>(B, xp.tw, nb, xp.pl.sub[st], xp.pl.radix[st], 1, nb, tid, nthr);
+            stage_dispatch_dual_small<true>(B, xp.tw, nb, xp.pl.sub[st], xp.pl.radix[st], tid, nthr);
             __syncthreads();
         }
         const float mu = xp.normalize ? (float)mu_over_m[t] : 0.f;
         float* o = out + (size_t)t * out_tpl_stride + (size_t)row * ns;
 #define D4W_CALL(R) xcorrd_first_inv_out<R>(B, Pc, Pf, xp.tw, nb, V, t0, ns, mu, xp.normalize != 0, o, tid, nthr);
-        D4W_ROW_RADIX_SWITCH(r0, D4W_CALL)
+        D4W_SMALL_RADIX_SWITCH(r0, D4W_CALL)
 #undef D4W_CALL
         __syncthreads();
     }
@@ -594,65 +610,97 @@ __device__ __forceinline__ float ext_value(const float* __restrict__ r, int e, i
 // direction of travel and starts `warm` samples earlier from a zero state; the poles' decay (host picks
 // warm so that |p|max^warm < 1e-9) makes the result identical to the sequential recursion at fp32
 // precision.  Chunk 0 starts from SciPy's steady-state initial condition zi * first sample.
-template <int DIR>
-static __global__ void __launch_bounds__(32)
+// NSEC = compile-time section count (0: generic, runtime count up to kMaxSections); NCH = time chunks a warp walks
+// at once (independent recursions interleaved instruction by instruction -> twice the DFMA chains in flight per lane).
+// Block = 4 warps, each warp its own (32 channels, NCH chunks) work item.
+template <int DIR, int NSEC, int NCH>
+static __global__ void __launch_bounds__(128)
 k_sos_pass(SosParams sp, const float* __restrict__ x, float* __restrict__ tmp, float* __restrict__ y, int nx, int chunk,
-           int warm) {
-    __shared__ float tile[32][33];
-    const int lane = threadIdx.x;
-    const int ch0 = blockIdx.x * 32;
+           int warm, int nchunks) {
+    __shared__ float tile_all[4][NCH][32][33];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    float (*tile)[32][33] = tile_all[wid];
+    const int ch0 = (blockIdx.x * 4 + wid) * 32;
+    if (ch0 >= nx) return;
     const int ns = sp.ns, pad = sp.pad, next = ns + 2 * pad;
     const int ch = ch0 + lane;
     const bool live = ch < nx;
+    constexpr int NS_ = NSEC > 0 ? NSEC : kMaxSections;
+    const int nsec = NSEC > 0 ? NSEC : sp.nsec;
     // progress index p = 0..next-1 along the direction of travel; extended index e = p (fwd) or next-1-p (bwd)
-    const int p_lo = (chunk > 0) ? (int)blockIdx.y * chunk : 0;            // first sample this block must OUTPUT
-    const int p_hi = (chunk > 0) ? min(next, p_lo + chunk) : next;
-    const int p_start = (chunk > 0 && blockIdx.y > 0) ? max(0, p_lo - warm) : 0;
-    if (p_lo >= next) return;
-    double z0[kMaxSections], z1[kMaxSections];
-    float first = 0.f;
-    if (live && p_start == 0) {
-        if (DIR > 0) first = ext_value(x + (size_t)ch * ns, 0, pad, ns);
-        else first = tmp[(size_t)ch * next + (next - 1)];
-    }
+    int p_lo[NCH], p_hi[NCH], p_cur[NCH];
+    double z0[NCH][NS_], z1[NCH][NS_];
+    int steps = 0;
 #pragma unroll
-    for (int s = 0; s < kMaxSections; ++s) { z0[s] = sp.zi0[s] * (double)first; z1[s] = sp.zi1[s] * (double)first; }
-    for (int p0 = p_start; p0 < p_hi; p0 += 32) {
+    for (int k = 0; k < NCH; ++k) {
+        const int cidx = (int)blockIdx.y * NCH + k;
+        if (chunk > 0) { p_lo[k] = cidx * chunk; p_hi[k] = min(next, p_lo[k] + chunk); }
+        else { p_lo[k] = (cidx == 0) ? 0 : next; p_hi[k] = next; }
+        if (cidx >= nchunks) p_lo[k] = p_hi[k] = next;                      // idle slot
+        const int p_start = (chunk > 0 && cidx > 0) ? max(0, p_lo[k] - warm) : p_lo[k];
+        p_cur[k] = (cidx >= nchunks) ? next : min(p_start, p_hi[k]);
+        float first = 0.f;
+        if (live && p_start == 0 && p_lo[k] < next) {
+            if (DIR > 0) first = ext_value(x + (size_t)ch * ns, 0, pad, ns);
+            else first = tmp[(size_t)ch * next + (next - 1)];
+        }
+#pragma unroll
+        for (int s = 0; s < NS_; ++s) { z0[k][s] = sp.zi0[s] * (double)first; z1[k][s] = sp.zi1[s] * (double)first; }
+        steps = max(steps, (p_hi[k] - p_cur[k] + 31) / 32);
+    }
+    for (int it = 0; it < steps; ++it) {
         // stage in: lane = progress offset, loop over channels
-        for (int c = 0; c < 32; ++c) {
-            const int cc = ch0 + c;
-            const int p = p0 + lane;
-            const int e = (DIR > 0) ? p : next - 1 - p;
-            float v = 0.f;
-            if (cc < nx && p < p_hi) v = (DIR > 0) ? ext_value(x + (size_t)cc * ns, e, pad, ns) : tmp[(size_t)cc * next + e];
-            tile[c][lane] = v;
+#pragma unroll
+        for (int k = 0; k < NCH; ++k) {
+            const int p = p_cur[k] + lane;
+#pragma unroll 8
+            for (int c = 0; c < 32; ++c) {
+                const int cc = ch0 + c;
+                const int e = (DIR > 0) ? p : next - 1 - p;
+                float v = 0.f;
+                if (cc < nx && p < p_hi[k]) v = (DIR > 0) ? ext_value(x + (size_t)cc * ns, e, pad, ns) : tmp[(size_t)cc * next + e];
+                tile[k][c][lane] = v;
+            }
         }
         __syncwarp();
         if (live) {
-            const int qn = min(32, p_hi - p0);
-            for (int q = 0; q < qn; ++q) {
-                double v = (double)tile[lane][q];
+#pragma unroll 4
+            for (int q = 0; q < 32; ++q) {
+                double v[NCH];
 #pragma unroll
-                for (int s = 0; s < kMaxSections; ++s) {
-                    if (s < sp.nsec) {
-                        const double o = fma(sp.b0[s], v, z0[s]);
-                        z0[s] = fma(sp.b1[s], v, fma(-sp.a1[s], o, z1[s]));
-                        z1[s] = fma(sp.b2[s], v, -sp.a2[s] * o);
-                        v = o;
+                for (int k = 0; k < NCH; ++k) v[k] = (double)tile[k][lane][q];
+#pragma unroll
+                for (int s = 0; s < NS_; ++s) {
+                    if (NSEC > 0 || s < nsec) {
+#pragma unroll
+                        for (int k = 0; k < NCH; ++k) {
+                            const double o = fma(sp.b0[s], v[k], z0[k][s]);
+                            z0[k][s] = fma(sp.b1[s], v[k], fma(-sp.a1[s], o, z1[k][s]));
+                            z1[k][s] = fma(sp.b2[s], v[k], -sp.a2[s] * o);
+                            v[k] = o;
+                        }
                     }
                 }
-                tile[lane][q] = (float)v;
+#pragma unroll
+                for (int k = 0; k < NCH; ++k) tile[k][lane][q] = (float)v[k];
             }
         }
         __syncwarp();
-        for (int c = 0; c < 32; ++c) {
-            const int cc = ch0 + c;
-            const int p = p0 + lane;
-            if (cc < nx && p >= p_lo && p < p_hi) {
+#pragma unroll
+        for (int k = 0; k < NCH; ++k) {
+            const int p = p_cur[k] + lane;
+            if (p >= p_lo[k] && p < p_hi[k]) {
                 const int e = (DIR > 0) ? p : next - 1 - p;
-                if (DIR > 0) tmp[(size_t)cc * next + e] = tile[c][lane];
-                else { const int i = e - pad; if (i >= 0 && i < ns) y[(size_t)cc * ns + i] = tile[c][lane]; }
+#pragma unroll 8
+                for (int c = 0; c < 32; ++c) {
+                    const int cc = ch0 + c;
+                    if (cc < nx) {
+                        if (DIR > 0) tmp[(size_t)cc * next + e] = tile[k][c][lane];
+                        else { const int i = e - pad; if (i >= 0 && i < ns) y[(size_t)cc * ns + i] = tile[k][c][lane]; }
+                    }
+                }
             }
+            p_cur[k] = min(p_cur[k] + 32, p_hi[k] + 32);      // past p_hi: staged zeros, nothing written
         }
         __syncwarp();
     }

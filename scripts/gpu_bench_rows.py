@@ -48,3 +48,22 @@ def sc():
     with contextlib.redirect_stdout(io.StringIO()):
         return dw.detect.compute_cross_correlogram_spectrocorr(sub, FS, [14., 30.], kern, 0.8, 0.95)
 report("compute_cross_correlogram_spectrocorr on 2000 ch", timeit(sc, reps=1) * NX / 2000, 4 * S, "scaled from 2000 channels")
+# ---- round 2 additions ------------------------------------------------------------------------------------------------
+corr = rows.cross_correlogram(x, [hf])[0]
+env = rows.envelope(corr)
+thr = 0.5 * float(env.max())
+report("find_peaks flags (detection threshold)", timeit(lambda: rows.find_peaks_flags(env, thr)), 5 * S)
+flags = rows.find_peaks_flags(env, thr)
+report("compact_picks (device)", timeit(lambda: rows.compact_picks(flags)), S, "%d picks" % int(flags.sum()))
+del corr, env, flags; torch.cuda.empty_cache()
+raw = (x * 5.0e4).round().to(torch.int32)
+report("raw2strain int32 -> fp32", timeit(lambda: rows.raw2strain(raw, 1e-9)), 8 * S)
+del raw; torch.cuda.empty_cache()
+report("get_fx[nfft 8192] ", timeit(lambda: dw.dsp.get_fx(x[:, :8192].contiguous(), 8192)), 8 * NX * 8192)
+with contextlib.redirect_stdout(io.StringIO()):
+    t_gab = timeit(lambda: dw.improcess.gabor_detect(x, FS, DX, [0, NX, 1], threshold=9100., threshold2=150.), reps=1)
+report("improcess.gabor_detect (trace2image .. masked trace)", t_gab, 12 * S, "envelope/std + minmax + 1/10 binning + 2 x 101x101 filter2D pair + upsample-multiply")
+img = dw.improcess.binning(dw.improcess.trace2image(x), 1 / 10, 1 / 10)
+up, down = dw.improcess.gabor_filt_design(74.77)
+report("filter2D 101x101 on the binned image", timeit(lambda: dw.improcess.filter2D(img, None, up + down)), 8 * img.numel(),
+       "%d x %d image, %.2f GFMA" % (img.shape[0], img.shape[1], img.numel() * 10201 / 1e9))
