@@ -18,6 +18,8 @@ struct d4w_fft_plan {
     int fused = 0;               // k_xcorr_fused usable: >= 2 stages, first and last stage in-register radices
     float2* d_tw = nullptr;
     int* d_k2pos = nullptr;
+    int pfa = 0;                 // n == 2520: prime-factor blocks of the matched filter (fft_pfa.cuh)
+    int* d_tpos = nullptr;       // pfa: position of time index i
 };
 
 extern "C" int d4w_fft_plan_create(d4w_fft_plan** out, int n, int device) {
@@ -51,10 +53,21 @@ extern "C" int d4w_fft_plan_create(d4w_fft_plan** out, int n, int device) {
                 for (int j = 0; j < G; ++j) p->tab2k[(size_t)m * G + j] = p->pos2k[(size_t)j * rl + m];
         }
     }
+    std::vector<int> tpos;
+    if (n == kPfaN && env_int("D4W_XCORR_PFA", 1)) {
+        // prime-factor plan: positions are [5][7][8][9] digits; table order of the fused last dimension (radix 9)
+        p->pfa = 1; p->fused = 0;
+        pfa_build_maps(tpos, p->pos2k);
+        p->tab2k.assign((size_t)n, 0);
+        const int G = n / 9;
+        for (int m = 0; m < 9; ++m)
+            for (int j = 0; j < G; ++j) p->tab2k[(size_t)m * G + j] = p->pos2k[(size_t)j * 9 + m];
+    }
     std::vector<int> k2pos((size_t)n);
     for (int i = 0; i < n; ++i) k2pos[p->pos2k[i]] = i;
     cudaError_t e = upload(&p->d_tw, make_twiddles(n));
     if (e == cudaSuccess) e = upload(&p->d_k2pos, k2pos);
+    if (e == cudaSuccess && p->pfa) e = upload(&p->d_tpos, tpos);
     if (e != cudaSuccess) { d4w_fft_plan_destroy(p); return fail(D4W_ERR_CUDA, std::string("fft plan: ") + cudaGetErrorString(e)); }
     *out = p;
     return D4W_OK;
@@ -63,7 +76,7 @@ extern "C" int d4w_fft_plan_create(d4w_fft_plan** out, int n, int device) {
 extern "C" int d4w_fft_plan_destroy(d4w_fft_plan* p) {
     if (!p) return D4W_OK;
     DeviceGuard guard(p->device);
-    cudaFree(p->d_tw); cudaFree(p->d_k2pos);
+    cudaFree(p->d_tw); cudaFree(p->d_k2pos); cudaFree(p->d_tpos);
     delete p;
     return D4W_OK;
 }
@@ -119,6 +132,15 @@ extern "C" int d4w_xcorr(d4w_fft_plan* p, const float* x, int nx, int ns, int va
     xp.nseg = (ns + valid - 1) / valid;
     // dual-lane kernel (four segments per CTA, packed f32x2 butterflies): needs the fused plan shape; 2 CTAs per SM
     const size_t smem_dual = (size_t)2 * p->n * 16 + (size_t)((valid + 7) / 8) * 16 + (size_t)valid * 8 + 16;
+    if (p->pfa) {
+        D4W_CUDA_TRY(cudaFuncSetAttribute(k_xcorr_pfa, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+        if (smem_dual > 112 * 1024) return fail(D4W_ERR_UNSUPPORTED, "d4w_xcorr: shared memory");
+        dim3 gridp((xp.nseg + 3) / 4, nx);
+        k_xcorr_pfa<<<gridp, 256, smem_dual, (cudaStream_t)stream>>>(xp, p->d_tpos, x, (const float2*)dev_tabs, dev_stats, dev_segpre,
+                                                                    dev_mu_over_m, out, (size_t)nx * ns);
+        D4W_CHECK_LAUNCH("k_xcorr_pfa");
+        return D4W_OK;
+    }
     bool small_radices = true;
     for (int st = 0; st < p->pl.nstages; ++st) small_radices = small_radices && xcorr_dual_radix_ok(p->pl.radix[st]);
     if (p->fused && p->pl.nstages >= 2 && small_radices && smem_dual <= 110 * 1024 && env_int("D4W_XCORR_DUAL", 1)) {

@@ -122,6 +122,35 @@ template <bool INV> struct DFTD<5, INV> {
     }
 };
 
+// radix 7 (prime): pair terms t_j = v[j] + v[7-j], d_j = v[j] - v[7-j]; X_m = A_m -/+ i B_m with
+// A_m = v0 + sum_j cos(2 pi j m / 7) t_j, B_m = sum_j sin(2 pi j m / 7) d_j (forward: X_m = A_m - i B_m, X_{7-m} = A_m + i B_m).
+// Used by the prime-factor (Good-Thomas) 2520-point blocks of the matched filter.
+template <bool INV> struct DFTD<7, INV> {
+    static D4W_HD void run(cpd (&v)[7]) {
+        constexpr float c1 = 0.62348980185873353053f, c2 = -0.22252093395631440429f, c3 = -0.90096886790241912624f;
+        constexpr float s1 = 0.78183148246802980871f, s2 = 0.97492791218182360702f, s3 = 0.43388373911755812048f;
+        const cpd t1 = dadd(v[1], v[6]), d1 = dsub(v[1], v[6]);
+        const cpd t2 = dadd(v[2], v[5]), d2 = dsub(v[2], v[5]);
+        const cpd t3 = dadd(v[3], v[4]), d3 = dsub(v[3], v[4]);
+        const cpd a0 = v[0];
+        v[0] = dadd(a0, dadd(t1, dadd(t2, t3)));
+        // cos(2 pi j m / 7) for (m, j): m = 1: c1 c2 c3;  m = 2: c2 c3 c1;  m = 3: c3 c1 c2
+        // sin(2 pi j m / 7):           m = 1: s1 s2 s3;  m = 2: s2 -s3 -s1; m = 3: s3 -s1 s2
+        const cpd A1 = dmake(vfma(t1.x, vbc(c1), vfma(t2.x, vbc(c2), vfma(t3.x, vbc(c3), a0.x))), vfma(t1.y, vbc(c1), vfma(t2.y, vbc(c2), vfma(t3.y, vbc(c3), a0.y))));
+        const cpd A2 = dmake(vfma(t1.x, vbc(c2), vfma(t2.x, vbc(c3), vfma(t3.x, vbc(c1), a0.x))), vfma(t1.y, vbc(c2), vfma(t2.y, vbc(c3), vfma(t3.y, vbc(c1), a0.y))));
+        const cpd A3 = dmake(vfma(t1.x, vbc(c3), vfma(t2.x, vbc(c1), vfma(t3.x, vbc(c2), a0.x))), vfma(t1.y, vbc(c3), vfma(t2.y, vbc(c1), vfma(t3.y, vbc(c2), a0.y))));
+        const cpd B1 = dmake(vfma(d1.x, vbc(s1), vfma(d2.x, vbc(s2), vmul(d3.x, vbc(s3)))), vfma(d1.y, vbc(s1), vfma(d2.y, vbc(s2), vmul(d3.y, vbc(s3)))));
+        const cpd B2 = dmake(vfma(d1.x, vbc(s2), vfma(d2.x, vbc(-s3), vmul(d3.x, vbc(-s1)))), vfma(d1.y, vbc(s2), vfma(d2.y, vbc(-s3), vmul(d3.y, vbc(-s1)))));
+        const cpd B3 = dmake(vfma(d1.x, vbc(s3), vfma(d2.x, vbc(-s1), vmul(d3.x, vbc(s2)))), vfma(d1.y, vbc(s3), vfma(d2.y, vbc(-s1), vmul(d3.y, vbc(s2)))));
+        // forward: A - i B = (A.x + B.y, A.y - B.x);  A + i B = (A.x - B.y, A.y + B.x); inverse swaps the two
+        const cpd p1 = dmake(vadd(A1.x, B1.y), vsub(A1.y, B1.x)), q1 = dmake(vsub(A1.x, B1.y), vadd(A1.y, B1.x));
+        const cpd p2 = dmake(vadd(A2.x, B2.y), vsub(A2.y, B2.x)), q2 = dmake(vsub(A2.x, B2.y), vadd(A2.y, B2.x));
+        const cpd p3 = dmake(vadd(A3.x, B3.y), vsub(A3.y, B3.x)), q3 = dmake(vsub(A3.x, B3.y), vadd(A3.y, B3.x));
+        if constexpr (!INV) { v[1] = p1; v[6] = q1; v[2] = p2; v[5] = q2; v[3] = p3; v[4] = q3; }
+        else { v[1] = q1; v[6] = p1; v[2] = q2; v[5] = p2; v[3] = q3; v[4] = p3; }
+    }
+};
+
 // Composite radix, IN PLACE with permuted output: R = R1*R2 (both factors are base radices for every
 // radix we use), input v[n] natural; on return X[m] sits at v[outpos<R>(m)].  No second register
 // array: the R2 length-R1 column DFTs, the internal twiddles and the R1 length-R2 row DFTs all

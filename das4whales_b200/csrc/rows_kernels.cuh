@@ -8,6 +8,7 @@
 //   dsp.get_spectrogram / detect.get_sliced_nspectrogram     dsp.py:41-78, detect.py:334-408
 #pragma once
 #include <cuda_fp16.h>
+#include "fft_pfa.cuh"
 #include <type_traits>
 #include "fft_smem.cuh"
 #include "fk_kernels.cuh"
@@ -427,6 +428,102 @@ k_xcorr_dual(XcorrParams xp, const float* __restrict__ x, const float2* __restri
 #define D4W_CALL(R) xcorrd_first_inv_out<R>(B, Pc, Pf, xp.tw, nb, V, t0, ns, mu, xp.normalize != 0, o, tid, nthr);
         D4W_SMALL_RADIX_SWITCH(r0, D4W_CALL)
 #undef D4W_CALL
+        __syncthreads();
+    }
+}
+
+// ---- prime-factor variant (blocks of 2520 = 5 * 7 * 8 * 9 samples, fft_pfa.cuh): same four-segments-per-CTA dual-lane layout,
+// but no twiddle factors between the stages and conflict-free strides.  The block is loaded in natural time order (B),
+// prefix-summed, scattered to the 4-D positions (S), transformed, and the result is gathered back to time order on the way out
+// so that every global access stays coalesced.  tabs[t][m * 280 + j] belongs to position j * 9 + m (d4w_fft_plan_table_order).
+static __global__ void __launch_bounds__(256, 2)
+k_xcorr_pfa(XcorrParams xp, const int* __restrict__ tpos, const float* __restrict__ x, const float2* __restrict__ tabs,
+            const double* __restrict__ stats, const double* __restrict__ segpre, const double* __restrict__ mu_over_m,
+            float* __restrict__ out, size_t out_tpl_stride) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    constexpr int nb = kPfaN;
+    const int ns = xp.ns, V = xp.valid;
+    const int ng = (V + 7) >> 3;
+    cpd* S = reinterpret_cast<cpd*>(smraw);
+    cpd* B = S + nb;
+    float4* Pc = reinterpret_cast<float4*>(B + nb);
+    half4* Pf = reinterpret_cast<half4*>(Pc + ng);
+    __shared__ float4 s_wsum[8];
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, wid = tid >> 5;
+    const int row = blockIdx.y;
+    const int seg0 = 4 * blockIdx.x;
+    const int t0 = seg0 * V;
+    const float* r = x + (size_t)row * ns;
+    float mean = 0.f, inv = 1.f;
+    if (xp.normalize) { mean = (float)stats[4 * (size_t)row]; inv = (float)(1.0 / stats[4 * (size_t)row + 1]); }
+    for (int i = tid; i < nb; i += nthr) {
+        const int ia = t0 + i, ib = ia + V, ic = ib + V, id = ic + V;
+        const float a = (ia < ns) ? (r[ia] - mean) * inv : 0.f;
+        const float b = (ib < ns) ? (r[ib] - mean) * inv : 0.f;
+        const float c = (ic < ns) ? (r[ic] - mean) * inv : 0.f;
+        const float d = (id < ns) ? (r[id] - mean) * inv : 0.f;
+        B[i] = dmake(f2x_set(a, c), f2x_set(b, d));
+    }
+    __syncthreads();
+    if (xp.normalize) {
+        const int gpt = (ng + nthr - 1) / nthr;
+        const int g0 = min(ng, tid * gpt), g1 = min(ng, g0 + gpt);
+        float4 loc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = g0 * 8; i < min(V, g1 * 8); ++i) {
+            const cpd z = B[i];
+            loc.x += f2x_lo(z.x); loc.y += f2x_lo(z.y); loc.z += f2x_hi(z.x); loc.w += f2x_hi(z.y);
+        }
+        float4 inc = loc;
+        for (int o = 1; o < 32; o <<= 1) {
+            const float ux = __shfl_up_sync(0xffffffffu, inc.x, o), uy = __shfl_up_sync(0xffffffffu, inc.y, o);
+            const float uz = __shfl_up_sync(0xffffffffu, inc.z, o), uw = __shfl_up_sync(0xffffffffu, inc.w, o);
+            if (lane >= o) { inc.x += ux; inc.y += uy; inc.z += uz; inc.w += uw; }
+        }
+        if (lane == 31) s_wsum[wid] = inc;
+        __syncthreads();
+        float4 run = make_float4(inc.x - loc.x, inc.y - loc.y, inc.z - loc.z, inc.w - loc.w);
+        for (int w = 0; w < wid; ++w) { run.x += s_wsum[w].x; run.y += s_wsum[w].y; run.z += s_wsum[w].z; run.w += s_wsum[w].w; }
+        const size_t sp = (size_t)row * xp.nseg + seg0;
+        run.x += (seg0 + 0 < xp.nseg) ? (float)segpre[sp + 0] : 0.f;
+        run.y += (seg0 + 1 < xp.nseg) ? (float)segpre[sp + 1] : 0.f;
+        run.z += (seg0 + 2 < xp.nseg) ? (float)segpre[sp + 2] : 0.f;
+        run.w += (seg0 + 3 < xp.nseg) ? (float)segpre[sp + 3] : 0.f;
+        for (int g = g0; g < g1; ++g) {
+            Pc[g] = run;
+            float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = g * 8; i < min(V, g * 8 + 8); ++i) {
+                half4 h; h.ac = __floats2half2_rn(f.x, f.z); h.bd = __floats2half2_rn(f.y, f.w);
+                Pf[i] = h;
+                const cpd z = B[i];
+                f.x += f2x_lo(z.x); f.y += f2x_lo(z.y); f.z += f2x_hi(z.x); f.w += f2x_hi(z.y);
+            }
+            run.x += f.x; run.y += f.y; run.z += f.z; run.w += f.w;
+        }
+    }
+    for (int i = tid; i < nb; i += nthr) S[tpos[i]] = B[i];          // time order -> [5][7][8][9] positions
+    __syncthreads();
+    pfa_forward_3(S, tid, nthr);
+    for (int t = 0; t < xp.ntpl; ++t) {
+        pfa_last_fused(S, B, tabs + (size_t)t * nb, tid, nthr);
+        __syncthreads();
+        pfa_inverse_3(B, tid, nthr);
+        const float mu = xp.normalize ? (float)mu_over_m[t] : 0.f;
+        float* o = out + (size_t)t * out_tpl_stride + (size_t)row * ns;
+        for (int i = tid; i < V; i += nthr) {
+            const cpd z = B[tpos[i]];
+            float va = f2x_lo(z.x), vc = f2x_hi(z.x), vb = f2x_lo(z.y), vd = f2x_hi(z.y);
+            if (xp.normalize) {
+                const float4 c = Pc[i >> 3];
+                const half4 f = Pf[i];
+                const float2 fac = __half22float2(f.ac), fbd = __half22float2(f.bd);
+                va += mu * (c.x + fac.x); vb += mu * (c.y + fbd.x); vc += mu * (c.z + fac.y); vd += mu * (c.w + fbd.y);
+            }
+            const int ta = t0 + i, tb = ta + V, tc = tb + V, td = tc + V;
+            if (ta < ns) o[ta] = va;
+            if (tb < ns) o[tb] = vb;
+            if (tc < ns) o[tc] = vc;
+            if (td < ns) o[td] = vd;
+        }
         __syncthreads();
     }
 }

@@ -1,6 +1,8 @@
 """Per-channel (row) operators on the GPU: row statistics, overlap-save matched filter, Hilbert
 envelope / SNR, forward-backward SOS IIR, batched STFT.  Thin host wrappers over libd4w.so
 (csrc/rows_kernels.cuh); inputs are contiguous float32 CUDA tensors [nx, ns]."""
+import os as _os
+
 import numpy as np
 import scipy.signal as sp
 
@@ -84,6 +86,9 @@ def _pick_block(L, ns=0):
     """Overlap-save block length.  Lengths of the form 2^a * 25 * 25 end in odd-radix stages, which keeps the
     8-byte shared-memory accesses of the last stages conflict-free (a power of two would end in a stride-16
     radix-16 stage: 6x the wavefronts); 2500 keeps three CTAs per SM with 94 % of each block valid."""
+    # 2520 = 5 * 7 * 8 * 9: prime-factor blocks (no twiddles, csrc/fft_pfa.cuh) -- the default for templates up to 315 taps
+    if L <= 2520 // 8 and not (ns and (ns + (2520 - L)) // (2520 - L + 1) > 512) and _os.environ.get("D4W_XCORR_PFA", "1") != "0":
+        return 2520
     for nb in (1250, 2500, 5000, 10000):
         if ns and (ns + (nb - L)) // (nb - L + 1) > 512 and nb < 10000:
             continue                                  # row statistics keep at most 512 segment prefixes per row

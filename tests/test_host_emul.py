@@ -39,6 +39,13 @@ def test_fft_engine_emulation(tmpdir_mod):
         assert r.returncode == 0 and "OK" in r.stdout, r.stdout
 
 
+def test_pfa_2520_engine_emulation(tmpdir_mod):
+    """prime-factor 2520-point transform of the matched filter (csrc/fft_pfa.cuh): radix 5/7/8/9 dual butterflies, CRT maps"""
+    exe = _build("pfa_emul", tmpdir_mod)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stdout
+
+
 def _run(exe, tmp, nx, ns, kind, taper, x, kval, fval, c, H=None, dense=None, col=(0, 0), env=None):
     fin, fout = os.path.join(tmp, "in.bin"), os.path.join(tmp, "out.bin")
     with open(fin, "wb") as f:
