@@ -334,9 +334,12 @@ extern "C" int d4w_sosfiltfilt(const float* x, float* y, float* tmp, int nx, int
     dim3 grid((blocks + 3) / 4, (nchunks + nch - 1) / nch);
 #define D4W_SOS(NS_, NCH_)                                                                               \
     do {                                                                                                 \
-        k_sos_pass<1, NS_, NCH_><<<grid, 128, 0, stream>>>(sp, x, tmp, y, nx, chunk, warm, nchunks);     \
+        const size_t sm_ = (size_t)4 * 2 * NCH_ * 32 * 33 * sizeof(float);                               \
+        D4W_CUDA_TRY(cudaFuncSetAttribute(k_sos_pass<1, NS_, NCH_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_));   \
+        D4W_CUDA_TRY(cudaFuncSetAttribute(k_sos_pass<-1, NS_, NCH_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_));  \
+        k_sos_pass<1, NS_, NCH_><<<grid, 128, sm_, stream>>>(sp, x, tmp, y, nx, chunk, warm, nchunks);   \
         D4W_CHECK_LAUNCH("k_sos_pass<fwd>");                                                             \
-        k_sos_pass<-1, NS_, NCH_><<<grid, 128, 0, stream>>>(sp, x, tmp, y, nx, chunk, warm, nchunks);    \
+        k_sos_pass<-1, NS_, NCH_><<<grid, 128, sm_, stream>>>(sp, x, tmp, y, nx, chunk, warm, nchunks);  \
         D4W_CHECK_LAUNCH("k_sos_pass<bwd>");                                                             \
     } while (0)
     if (nch == 2) {

@@ -58,7 +58,32 @@ __host__ __device__ inline void pfa_stage(cpd* __restrict__ s, int tid, int nthr
     }
 }
 
+// first forward stage (dimension a, radix 5) fused with the time-order -> position scatter: item (b, c, d) gathers its five
+// inputs straight from the time-ordered block T at n_a = (360 b + 315 c + 280 d + 504 a) mod 2520 and writes positions
+// (a, b, c, d) of S.  Threads run over c fastest: the gather stride is then 315 elements = 1260 words = 12 (mod 32) and the
+// store stride 9 elements = 4 (mod 32) -- both conflict-free for 16-byte accesses of a quarter warp.
+__host__ __device__ inline void pfa_first_from_time(const cpd* __restrict__ T, cpd* __restrict__ S, int tid, int nthr) {
+    for (int j = tid; j < 504; j += nthr) {
+        const int c = j & 7, bd = j >> 3;            // bd = b * 9 + d, 63 combinations
+        const int b = bd / 9, d = bd - 9 * b;
+        int n = (360 * b + 315 * c + 280 * d) % kPfaN;
+        cpd v[5];
+        static_for<5>([&](auto ac) {
+            constexpr int a = decltype(ac)::value;
+            v[a] = T[n];
+            n += 504; if (n >= kPfaN) n -= kPfaN;
+        });
+        DFTD<5, false>::run(v);
+        cpd* base = S + b * 72 + c * 9 + d;
+        static_for<5>([&](auto qc) { constexpr int q = decltype(qc)::value; base[q * 504] = v[outpos<5>(q)]; });
+    }
+}
+
 // forward over the first three dimensions (5, 7, 8); the last one (9, contiguous) is fused with the spectrum multiply
+__host__ __device__ inline void pfa_forward_23(cpd* s, int tid, int nthr) {       // after pfa_first_from_time
+    pfa_stage<7, 72, false>(s, tid, nthr); D4W_SYNC();
+    pfa_stage<8, 9, false>(s, tid, nthr); D4W_SYNC();
+}
 __host__ __device__ inline void pfa_forward_3(cpd* s, int tid, int nthr) {
     pfa_stage<5, 504, false>(s, tid, nthr); D4W_SYNC();
     pfa_stage<7, 72, false>(s, tid, nthr); D4W_SYNC();

@@ -448,61 +448,64 @@ k_xcorr_pfa(XcorrParams xp, const int* __restrict__ tpos, const float* __restric
     cpd* B = S + nb;
     float4* Pc = reinterpret_cast<float4*>(B + nb);
     half4* Pf = reinterpret_cast<half4*>(Pc + ng);
-    __shared__ float4 s_wsum[8];
-    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, wid = tid >> 5;
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31;
     const int row = blockIdx.y;
     const int seg0 = 4 * blockIdx.x;
     const int t0 = seg0 * V;
     const float* r = x + (size_t)row * ns;
     float mean = 0.f, inv = 1.f;
     if (xp.normalize) { mean = (float)stats[4 * (size_t)row]; inv = (float)(1.0 / stats[4 * (size_t)row + 1]); }
-    for (int i = tid; i < nb; i += nthr) {
+    // load + normalise in time order (B) and, in the same sweep, the prefix sums of the mu term: lanes 8k .. 8k+7 hold one
+    // prefix group, so a 3-step segmented shuffle scan gives the in-group exclusive prefix (Pf, fp16) and the group total
+    // (parked in Pc, turned into the exclusive prefix over groups below) -- no shared-memory traffic, no bank conflicts
+    for (int i0 = 0; i0 < nb; i0 += nthr) {                      // every lane runs every iteration (full-mask shuffles below)
+        const int i = i0 + tid;
+        const bool in = i < nb;
         const int ia = t0 + i, ib = ia + V, ic = ib + V, id = ic + V;
-        const float a = (ia < ns) ? (r[ia] - mean) * inv : 0.f;
-        const float b = (ib < ns) ? (r[ib] - mean) * inv : 0.f;
-        const float c = (ic < ns) ? (r[ic] - mean) * inv : 0.f;
-        const float d = (id < ns) ? (r[id] - mean) * inv : 0.f;
-        B[i] = dmake(f2x_set(a, c), f2x_set(b, d));
-    }
-    __syncthreads();
-    if (xp.normalize) {
-        const int gpt = (ng + nthr - 1) / nthr;
-        const int g0 = min(ng, tid * gpt), g1 = min(ng, g0 + gpt);
-        float4 loc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int i = g0 * 8; i < min(V, g1 * 8); ++i) {
-            const cpd z = B[i];
-            loc.x += f2x_lo(z.x); loc.y += f2x_lo(z.y); loc.z += f2x_hi(z.x); loc.w += f2x_hi(z.y);
-        }
-        float4 inc = loc;
-        for (int o = 1; o < 32; o <<= 1) {
-            const float ux = __shfl_up_sync(0xffffffffu, inc.x, o), uy = __shfl_up_sync(0xffffffffu, inc.y, o);
-            const float uz = __shfl_up_sync(0xffffffffu, inc.z, o), uw = __shfl_up_sync(0xffffffffu, inc.w, o);
-            if (lane >= o) { inc.x += ux; inc.y += uy; inc.z += uz; inc.w += uw; }
-        }
-        if (lane == 31) s_wsum[wid] = inc;
-        __syncthreads();
-        float4 run = make_float4(inc.x - loc.x, inc.y - loc.y, inc.z - loc.z, inc.w - loc.w);
-        for (int w = 0; w < wid; ++w) { run.x += s_wsum[w].x; run.y += s_wsum[w].y; run.z += s_wsum[w].z; run.w += s_wsum[w].w; }
-        const size_t sp = (size_t)row * xp.nseg + seg0;
-        run.x += (seg0 + 0 < xp.nseg) ? (float)segpre[sp + 0] : 0.f;
-        run.y += (seg0 + 1 < xp.nseg) ? (float)segpre[sp + 1] : 0.f;
-        run.z += (seg0 + 2 < xp.nseg) ? (float)segpre[sp + 2] : 0.f;
-        run.w += (seg0 + 3 < xp.nseg) ? (float)segpre[sp + 3] : 0.f;
-        for (int g = g0; g < g1; ++g) {
-            Pc[g] = run;
-            float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int i = g * 8; i < min(V, g * 8 + 8); ++i) {
-                half4 h; h.ac = __floats2half2_rn(f.x, f.z); h.bd = __floats2half2_rn(f.y, f.w);
-                Pf[i] = h;
-                const cpd z = B[i];
-                f.x += f2x_lo(z.x); f.y += f2x_lo(z.y); f.z += f2x_hi(z.x); f.w += f2x_hi(z.y);
+        const float a = (in && ia < ns) ? (r[ia] - mean) * inv : 0.f;
+        const float b = (in && ib < ns) ? (r[ib] - mean) * inv : 0.f;
+        const float c = (in && ic < ns) ? (r[ic] - mean) * inv : 0.f;
+        const float d = (in && id < ns) ? (r[id] - mean) * inv : 0.f;
+        if (in) B[i] = dmake(f2x_set(a, c), f2x_set(b, d));
+        if (xp.normalize) {
+            float4 inc = make_float4(a, b, c, d);
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) {
+                const float ux = __shfl_up_sync(0xffffffffu, inc.x, o), uy = __shfl_up_sync(0xffffffffu, inc.y, o);
+                const float uz = __shfl_up_sync(0xffffffffu, inc.z, o), uw = __shfl_up_sync(0xffffffffu, inc.w, o);
+                if ((lane & 7) >= o) { inc.x += ux; inc.y += uy; inc.z += uz; inc.w += uw; }
             }
-            run.x += f.x; run.y += f.y; run.z += f.z; run.w += f.w;
+            if (i < V) { half4 h; h.ac = __floats2half2_rn(inc.x - a, inc.z - c); h.bd = __floats2half2_rn(inc.y - b, inc.w - d); Pf[i] = h; }
+            if ((lane & 7) == 7 && in && (i >> 3) < ng) Pc[i >> 3] = inc;
         }
     }
-    for (int i = tid; i < nb; i += nthr) S[tpos[i]] = B[i];          // time order -> [5][7][8][9] positions
     __syncthreads();
-    pfa_forward_3(S, tid, nthr);
+    if (xp.normalize && tid < 32) {
+        // exclusive scan of the group totals by one warp, seeded with the row prefix at the start of each segment
+        const size_t sp = (size_t)row * xp.nseg + seg0;
+        float4 carry;
+        carry.x = (seg0 + 0 < xp.nseg) ? (float)segpre[sp + 0] : 0.f;
+        carry.y = (seg0 + 1 < xp.nseg) ? (float)segpre[sp + 1] : 0.f;
+        carry.z = (seg0 + 2 < xp.nseg) ? (float)segpre[sp + 2] : 0.f;
+        carry.w = (seg0 + 3 < xp.nseg) ? (float)segpre[sp + 3] : 0.f;
+        for (int g0 = 0; g0 < ng; g0 += 32) {
+            const int g = g0 + lane;
+            const float4 own = (g < ng) ? Pc[g] : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 inc = own;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const float ux = __shfl_up_sync(0xffffffffu, inc.x, o), uy = __shfl_up_sync(0xffffffffu, inc.y, o);
+                const float uz = __shfl_up_sync(0xffffffffu, inc.z, o), uw = __shfl_up_sync(0xffffffffu, inc.w, o);
+                if (lane >= o) { inc.x += ux; inc.y += uy; inc.z += uz; inc.w += uw; }
+            }
+            if (g < ng) Pc[g] = make_float4(carry.x + inc.x - own.x, carry.y + inc.y - own.y, carry.z + inc.z - own.z, carry.w + inc.w - own.w);
+            carry.x += __shfl_sync(0xffffffffu, inc.x, 31); carry.y += __shfl_sync(0xffffffffu, inc.y, 31);
+            carry.z += __shfl_sync(0xffffffffu, inc.z, 31); carry.w += __shfl_sync(0xffffffffu, inc.w, 31);
+        }
+    }
+    pfa_first_from_time(B, S, tid, nthr);                       // radix-5 stage straight from the time-ordered block
+    __syncthreads();
+    pfa_forward_23(S, tid, nthr);
     for (int t = 0; t < xp.ntpl; ++t) {
         pfa_last_fused(S, B, tabs + (size_t)t * nb, tid, nthr);
         __syncthreads();
@@ -710,13 +713,23 @@ __device__ __forceinline__ float ext_value(const float* __restrict__ r, int e, i
 // NSEC = compile-time section count (0: generic, runtime count up to kMaxSections); NCH = time chunks a warp walks
 // at once (independent recursions interleaved instruction by instruction -> twice the DFMA chains in flight per lane).
 // Block = 4 warps, each warp its own (32 channels, NCH chunks) work item.
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
 template <int DIR, int NSEC, int NCH>
 static __global__ void __launch_bounds__(128)
 k_sos_pass(SosParams sp, const float* __restrict__ x, float* __restrict__ tmp, float* __restrict__ y, int nx, int chunk,
            int warm, int nchunks) {
-    __shared__ float tile_all[4][NCH][32][33];
+    // [warp][buffer][chunk][channel][time]: tiles are double-buffered -- the next 32-sample tile streams in with cp.async
+    // while the recursion runs on the current one (the recursion is a dependent fp64 chain: loads must not sit in front of it)
+    extern __shared__ float sos_sm[];
+    typedef float Tile[32][33];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    float (*tile)[32][33] = tile_all[wid];
+    Tile* tiles = reinterpret_cast<Tile*>(sos_sm) + (size_t)wid * 2 * NCH;      // tiles[buf * NCH + k]
     const int ch0 = (blockIdx.x * 4 + wid) * 32;
     if (ch0 >= nx) return;
     const int ns = sp.ns, pad = sp.pad, next = ns + 2 * pad;
@@ -745,27 +758,45 @@ k_sos_pass(SosParams sp, const float* __restrict__ x, float* __restrict__ tmp, f
         for (int s = 0; s < NS_; ++s) { z0[k][s] = sp.zi0[s] * (double)first; z1[k][s] = sp.zi1[s] * (double)first; }
         steps = max(steps, (p_hi[k] - p_cur[k] + 31) / 32);
     }
-    for (int it = 0; it < steps; ++it) {
-        // stage in: lane = progress offset, loop over channels
-#pragma unroll
-        for (int k = 0; k < NCH; ++k) {
-            const int p = p_cur[k] + lane;
+    // stage the tile that starts at progress index p0 of chunk k into buffer b (lane = progress offset, loop over channels)
+    auto stage = [&](int b, int k, int p0) {
+        Tile& t = tiles[b * NCH + k];
+        const int p = p0 + lane;
+        const bool full = (p0 + 32 <= p_hi[k]) && (nx - ch0 >= 32) && (DIR < 0 || (p0 >= pad && p0 + 32 <= pad + ns));
+        if (full) {
+            const float* src = (DIR > 0) ? x + (size_t)ch0 * ns + (p - pad) : tmp + (size_t)ch0 * next + (next - 1 - p);
+            const size_t pitch = (DIR > 0) ? (size_t)ns : (size_t)next;
 #pragma unroll 8
+            for (int c = 0; c < 32; ++c) cp_async4(&t[c][lane], src + (size_t)c * pitch);
+        } else {
+#pragma unroll 4
             for (int c = 0; c < 32; ++c) {
                 const int cc = ch0 + c;
                 const int e = (DIR > 0) ? p : next - 1 - p;
                 float v = 0.f;
                 if (cc < nx && p < p_hi[k]) v = (DIR > 0) ? ext_value(x + (size_t)cc * ns, e, pad, ns) : tmp[(size_t)cc * next + e];
-                tile[k][c][lane] = v;
+                t[c][lane] = v;
             }
         }
+    };
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) stage(0, k, p_cur[k]);
+    cp_async_commit();
+    for (int it = 0; it < steps; ++it) {
+        const int b = it & 1;
+        if (it + 1 < steps) {
+#pragma unroll
+            for (int k = 0; k < NCH; ++k) stage(b ^ 1, k, min(p_cur[k] + 32, p_hi[k] + 32));
+        }
+        cp_async_commit();
+        cp_async_wait_group<1>();                 // everything but the group just committed has landed
         __syncwarp();
         if (live) {
 #pragma unroll 4
             for (int q = 0; q < 32; ++q) {
                 double v[NCH];
 #pragma unroll
-                for (int k = 0; k < NCH; ++k) v[k] = (double)tile[k][lane][q];
+                for (int k = 0; k < NCH; ++k) v[k] = (double)tiles[b * NCH + k][lane][q];
 #pragma unroll
                 for (int s = 0; s < NS_; ++s) {
                     if (NSEC > 0 || s < nsec) {
@@ -779,7 +810,7 @@ k_sos_pass(SosParams sp, const float* __restrict__ x, float* __restrict__ tmp, f
                     }
                 }
 #pragma unroll
-                for (int k = 0; k < NCH; ++k) tile[k][lane][q] = (float)v[k];
+                for (int k = 0; k < NCH; ++k) tiles[b * NCH + k][lane][q] = (float)v[k];
             }
         }
         __syncwarp();
@@ -792,8 +823,8 @@ k_sos_pass(SosParams sp, const float* __restrict__ x, float* __restrict__ tmp, f
                 for (int c = 0; c < 32; ++c) {
                     const int cc = ch0 + c;
                     if (cc < nx) {
-                        if (DIR > 0) tmp[(size_t)cc * next + e] = tile[k][c][lane];
-                        else { const int i = e - pad; if (i >= 0 && i < ns) y[(size_t)cc * ns + i] = tile[k][c][lane]; }
+                        if (DIR > 0) tmp[(size_t)cc * next + e] = tiles[b * NCH + k][c][lane];
+                        else { const int i = e - pad; if (i >= 0 && i < ns) y[(size_t)cc * ns + i] = tiles[b * NCH + k][c][lane]; }
                     }
                 }
             }
@@ -801,6 +832,7 @@ k_sos_pass(SosParams sp, const float* __restrict__ x, float* __restrict__ tmp, f
         }
         __syncwarp();
     }
+    cp_async_wait_group<0>();
 }
 
 // ------------------------------------------------------------------ batched STFT magnitude (librosa.stft framing)

@@ -43,6 +43,18 @@ def test_signatures_match_reference_defaults():
     assert list(inspect.signature(dw.detect.gen_template_fincall).parameters) == ["time", "fs", "fmin", "fmax", "duration", "window"]
     assert list(inspect.signature(dw.detect.compute_cross_correlogram_spectrocorr).parameters) == \
         ["data", "fs", "flims", "kernel", "win_size", "overlap_pct"]
+    assert list(inspect.signature(dw.dsp.get_fx).parameters) == ["trace", "nfft"]
+    assert list(inspect.signature(dw.dsp.instant_freq).parameters) == ["channel", "fs"]
+    assert list(inspect.signature(dw.detect.xcorr).parameters) == ["t", "f", "Sxx", "tvec", "fvec", "BlueKernel"]
+    assert list(inspect.signature(dw.detect.nxcorr2d).parameters) == ["spectro", "kernel"]
+    assert list(inspect.signature(dw.detect.process_corr).parameters) == ["corr", "threshold"]
+    assert list(inspect.signature(dw.detect.pick_times_par).parameters) == ["corr_m", "threshold"]
+    assert list(inspect.signature(dw.improcess.trace2image).parameters) == ["trace"]
+    assert list(inspect.signature(dw.improcess.gabor_filt_design).parameters) == ["theta_c0", "plot"]
+    assert list(inspect.signature(dw.improcess.binning).parameters) == ["image", "ft", "fx"]
+    assert list(inspect.signature(dw.improcess.angle_fromspeed).parameters) == ["c0", "fs", "dx", "selected_channels"]
+    sig = inspect.signature(dw.improcess.apply_smooth_mask)
+    assert list(sig.parameters) == ["array", "mask", "sigma"] and sig.parameters["sigma"].default == 1.5
     # north-star aliases
     assert dw.dsp.bandpass is dw.dsp.bp_filt and dw.dsp.compute_spectrogram is dw.dsp.get_spectrogram
     assert dw.detect.matched_filter is dw.detect.compute_cross_correlogram
@@ -76,6 +88,13 @@ def test_butterworth_and_taper_kat(golden):
     assert np.array_equal(y, x * sp.windows.tukey(400, alpha=0.03)[None, :])
 
 
+def test_gabor_kernel_design_is_the_opencv_kernel(golden):
+    """improcess.gabor_filt_design restates cv2.getGaborKernel on the host (no OpenCV in the product path)."""
+    g = golden("gabor")
+    up, down = dw.improcess.gabor_filt_design(float(g["theta"]))
+    assert up.shape == (101, 101) and np.max(np.abs(up - g["up"])) <= 1e-14 and np.array_equal(down, np.flipud(up))
+
+
 def test_bench_reference_arm_contract():
     """`bench.py --impl reference` (the CPU arm the driver runs first) prints one JSON line with the agreed keys, and the
     product arm refuses to run without a GPU instead of falling back to the CPU."""
@@ -89,7 +108,9 @@ def test_bench_reference_arm_contract():
                 "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert key in line, key
     assert line["impl"] == "reference" and line["unit"] == "channels/s" and line["value"] > 0
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] == 1 and "sample" in line["cpu_baseline"]
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] == os.cpu_count() and "sample" in line["cpu_baseline"]
+    assert line["cpu_baseline"]["single_thread"]["cores"] == 1 and line["cpu_baseline"]["single_thread"]["value"] > 0
+    assert line["steps"] >= 1 and line["config"]["workload"].startswith("synthetic 10000 ch x 120000 samp")
     assert line["e2e"]["value"] == line["value"] and line["e2e"]["h2d_bytes_per_step"] == 0
     import torch
     if not torch.cuda.is_available():

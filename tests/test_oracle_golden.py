@@ -135,3 +135,70 @@ def test_picks_and_raw2strain_match_golden(golden):
     r = golden("raw2strain")
     out = DH.raw2strain(r["raw"], {"scale_factor": float(r["scale_factor"])})
     assert rel_err(out, r["strain"])[0] <= 1e-15
+
+
+def test_round2_views_match_golden(golden):
+    """dsp.get_fx / instant_freq, detect.xcorr / nxcorr2d / process_corr, unequal-length shift_xcorr (tests/golden/views.npz)."""
+    g = golden("views")
+    for nfft in (512, 600, 1000):
+        assert rel_err(O.get_fx(g["fx_x"], nfft), g[f"fx_{nfft}"])[0] <= 1e-14
+    assert rel_err(O.instant_freq(g["if_x"], FS), g["if_y"])[0] <= 1e-12
+    assert rel_err(D.shift_xcorr(g["sx_a"], g["sx_b"]), g["sx_ab"])[0] <= 1e-13
+    assert rel_err(D.shift_xcorr(g["sx_a"], g["sx_c"]), g["sx_ac"])[0] <= 1e-13
+    assert rel_err(D.shift_nxcorr(g["sx_a"], g["sx_c"]), g["snx_ac"])[0] <= 1e-13
+    ts, cv = D.xcorr(g["xc_t"], g["xc_f"], g["xc_S"], g["xc_tvec"], g["xc_fvec"], g["xc_ker"])
+    assert np.array_equal(ts, g["xc_tscale"]) and rel_err(cv, g["xc_val"])[0] <= 1e-13
+    nf = len(g["xc_f"])
+    assert rel_err(D.nxcorr2d(g["xc_S"][:nf], g["xc_ker"]), g["nxc2d"])[0] <= 1e-12
+    assert np.array_equal(D.process_corr(g["pc_x"], 0.05), g["pc_idx"])
+
+
+def test_round2_gabor_oracle_matches_golden(golden):
+    """The image-domain detector restated on OpenCV / torchvision (oracle/improcess_oracle.py) against the outputs of the
+    unmodified reference functions (tests/golden/gabor.npz)."""
+    cv2 = pytest.importorskip("cv2")
+    pytest.importorskip("torchvision")
+    from oracle import improcess_oracle as IO
+    from oracle.make_golden import synth
+    g = golden("gabor")
+    trf = synth(int(g["nx"]), int(g["ns"]), seed=int(g["seed"]), ncalls=int(g["ncalls"]))
+    assert abs(float(np.sum(trf)) - float(g["x_checksum"])) <= 1e-6 * abs(float(g["x_checksum"]))
+    masked, parts = IO.gabor_detect(trf, FS, DX, [0, int(g["nx"]), 1], 1500., 10, float(g["thr"]), float(g["thr2"]))
+    assert rel_err(parts["imagebin"], g["imagebin"])[0] <= 1e-12
+    assert rel_err(parts["fimage"], g["fimage"])[0] <= 1e-12
+    assert np.array_equal(parts["mask"], g["mask"])
+    ms = np.unpackbits(g["mask_sparse_bits"])[: trf.size].reshape(trf.shape).astype(bool)
+    assert np.array_equal(parts["mask_sparse"], ms)
+    assert rel_err(masked[g["rows"]], g["masked_rows"])[0] <= 1e-13
+    assert np.max(np.abs(IO.gabor_filt_design(float(g["theta"]))[0] - g["up"])) <= 1e-15
+
+
+def test_torch_second_oracle_pinned_to_numpy_oracle():
+    """oracle/torch_oracle.py (the float64 whole-matrix oracle of tests/test_fullsize_gpu.py) == oracle/dsp_oracle.py on the CPU."""
+    import torch
+    from oracle import torch_oracle as TO
+    rng = np.random.default_rng(3)
+    for nx, ns in ((64, 400), (100, 1200), (63, 406)):
+        sel = [0, nx, 1]
+        assert np.array_equal(TO.fk_filter_design((nx, ns), sel, DX, FS).numpy(), np.asarray(O.fk_filter_design((nx, ns), sel, DX, FS)))
+        args = (1350., 1450., 3300, 3450, 14., 30.)
+        mo = O.hybrid_ninf_filter_design((nx, ns), sel, DX, FS, *args)
+        assert np.max(np.abs(TO.hybrid_ninf_filter_design((nx, ns), sel, DX, FS, *args).numpy() - mo)) <= 1e-15
+        x = rng.standard_normal((nx, ns))
+        y = TO.fk_filter_filt(torch.from_numpy(x), torch.from_numpy(mo)).numpy()
+        assert rel_err(y, O.fk_filter_filt(x, mo))[0] <= 1e-13
+        assert rel_err(O.fk_filter_filt(x, mo, workers=2), O.fk_filter_filt(x, mo))[0] <= 1e-13     # bench's threaded CPU arm
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="/root/reference not present (GPU box)")
+def test_round2_oracle_against_live_reference():
+    dsp, detect = ref_loader.load()
+    imp = ref_loader.load_improcess()
+    from oracle import improcess_oracle as IO
+    rng = np.random.default_rng(8)
+    x = rng.standard_normal((30, 500))
+    assert rel_err(O.get_fx(x, 256), dsp.get_fx(x, 256))[0] <= 1e-14
+    assert rel_err(IO.trace2image(x), imp.trace2image(x))[0] <= 1e-13
+    assert rel_err(IO.binning(imp.trace2image(x), 0.1, 0.1), imp.binning(imp.trace2image(x), 0.1, 0.1))[0] <= 1e-13
+    up, down = imp.gabor_filt_design(40.0)
+    assert np.array_equal(up, IO.gabor_filt_design(40.0)[0]) and np.array_equal(down, IO.gabor_filt_design(40.0)[1])
