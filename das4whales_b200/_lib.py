@@ -59,7 +59,9 @@ def lib():
 def check(rc, what=""):
     if rc != 0:
         msg = ffi.string(lib().d4w_last_error()).decode(errors="replace")
-        if rc in (1, 2):
+        if rc == 2:
+            raise ValueError(f"{what}: {msg} (das4whales_b200.dsp.supported_shape(nx, ns) suggests the nearest supported shape)")
+        if rc == 1:
             raise ValueError(f"{what}: {msg}")
         raise D4WError(f"{what}: {msg} (status {rc})")
 

@@ -25,6 +25,19 @@ extern "C" int d4w_scale_pixels(const float* x, float* y, size_t n, float mul, v
     return D4W_OK;
 }
 
+extern "C" int d4w_db_re_max(const float* x, float* y, size_t n, void* dev_ws8, void* stream_v) {
+    if (!x || !y || !dev_ws8 || n < 1) return fail(D4W_ERR_ARG, "d4w_db_re_max: bad argument");
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    unsigned* mm = reinterpret_cast<unsigned*>(dev_ws8);
+    k_minmax_init<<<1, 1, 0, stream>>>(mm);
+    D4W_CHECK_LAUNCH("k_minmax_init");
+    k_minmax<<<grid1d(n, 256), 256, 0, stream>>>(x, n, mm);
+    D4W_CHECK_LAUNCH("k_minmax");
+    k_db_re_max<<<grid1d(n, 256, 148 * 32), 256, 0, stream>>>(x, y, n, mm);
+    D4W_CHECK_LAUNCH("k_db_re_max");
+    return D4W_OK;
+}
+
 extern "C" int d4w_resize_aa(const float* in, int ih, int iw, float* out, int oh, int ow, float* dev_tmp, void* stream_v) {
     if (!in || !out || !dev_tmp || ih < 1 || iw < 1 || oh < 1 || ow < 1) return fail(D4W_ERR_ARG, "d4w_resize_aa: bad argument");
     if (ih > 65535 || oh > 65535) return fail(D4W_ERR_UNSUPPORTED, "d4w_resize_aa: more than 65535 rows");

@@ -136,7 +136,7 @@ extern "C" int d4w_xcorr(d4w_fft_plan* p, const float* x, int nx, int ns, int va
         D4W_CUDA_TRY(cudaFuncSetAttribute(k_xcorr_pfa, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
         if (smem_dual > 112 * 1024) return fail(D4W_ERR_UNSUPPORTED, "d4w_xcorr: shared memory");
         dim3 gridp((xp.nseg + 3) / 4, nx);
-        k_xcorr_pfa<<<gridp, 256, smem_dual, (cudaStream_t)stream>>>(xp, p->d_tpos, x, (const float2*)dev_tabs, dev_stats, dev_segpre,
+        k_xcorr_pfa<<<gridp, kPfaThreads, smem_dual, (cudaStream_t)stream>>>(xp, p->d_tpos, x, (const float2*)dev_tabs, dev_stats, dev_segpre,
                                                                     dev_mu_over_m, out, (size_t)nx * ns);
         D4W_CHECK_LAUNCH("k_xcorr_pfa");
         return D4W_OK;

@@ -52,6 +52,14 @@ k_scale_pixels(const float* __restrict__ x, float* __restrict__ y, size_t n, con
         y[i] = (x[i] - lo) * inv * mul;
 }
 
+// y = 20 log10(x / max(x))   (dsp.get_spectrogram, dsp.py:76); mm[1] holds the maximum in the ordered-uint encoding
+static __global__ void __launch_bounds__(256)
+k_db_re_max(const float* __restrict__ x, float* __restrict__ y, size_t n, const unsigned* __restrict__ mm) {
+    const float inv = 1.0f / ord2f(mm[1]);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        y[i] = 20.0f * log10f(x[i] * inv);
+}
+
 // ---------------------------------------------------------------------------------- antialiased bilinear resize
 // One output index of ATen's separable `upsample_bilinear2d_aa` (align_corners = False, size given):
 //   scale = in / out; support = max(scale, 1); center = scale * (i + 0.5); xmin = max(int(center - support + 0.5), 0);

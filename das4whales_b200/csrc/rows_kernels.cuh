@@ -38,7 +38,15 @@ k_row_stats(const float* __restrict__ x, int ns, int seglen, int nseg, double* _
         for (int s = wid; s < nseg; s += 8) {
             const int a = s * seglen, b = min(ns, a + seglen);
             double ss = 0.0;
-            for (int i = a + lane; i < b; i += 32) {
+            int i = a + lane;
+            // four independent loads in flight per lane (the accumulation chain must not serialise the memory latency)
+            for (; i + 96 < b; i += 128) {
+                const float v0 = r[i], v1 = r[i + 32], v2 = r[i + 64], v3 = r[i + 96];
+                ss += ((double)v0 + (double)v1) + ((double)v2 + (double)v3);
+                sq += ((double)v0 * (double)v0 + (double)v1 * (double)v1) + ((double)v2 * (double)v2 + (double)v3 * (double)v3);
+                mx = fmaxf(fmaxf(mx, fmaxf(fabsf(v0), fabsf(v1))), fmaxf(fabsf(v2), fabsf(v3)));
+            }
+            for (; i < b; i += 32) {
                 const float v = r[i];
                 ss += (double)v; sq += (double)v * (double)v; mx = fmaxf(mx, fabsf(v));
             }
@@ -47,7 +55,15 @@ k_row_stats(const float* __restrict__ x, int ns, int seglen, int nseg, double* _
             sum += ss / 32.0;     // every lane adds 1/32 of the warp total -> warp reduction below restores it
         }
     } else {
-        for (int i = tid; i < ns; i += blockDim.x) {
+        int i = tid;
+        const int st = blockDim.x;
+        for (; i + 3 * st < ns; i += 4 * st) {
+            const float v0 = r[i], v1 = r[i + st], v2 = r[i + 2 * st], v3 = r[i + 3 * st];
+            sum += ((double)v0 + (double)v1) + ((double)v2 + (double)v3);
+            sq += ((double)v0 * (double)v0 + (double)v1 * (double)v1) + ((double)v2 * (double)v2 + (double)v3 * (double)v3);
+            mx = fmaxf(fmaxf(mx, fmaxf(fabsf(v0), fabsf(v1))), fmaxf(fabsf(v2), fabsf(v3)));
+        }
+        for (; i < ns; i += st) {
             const float v = r[i];
             sum += (double)v; sq += (double)v * (double)v; mx = fmaxf(mx, fabsf(v));
         }
@@ -436,7 +452,8 @@ k_xcorr_dual(XcorrParams xp, const float* __restrict__ x, const float2* __restri
 // but no twiddle factors between the stages and conflict-free strides.  The block is loaded in natural time order (B),
 // prefix-summed, scattered to the 4-D positions (S), transformed, and the result is gathered back to time order on the way out
 // so that every global access stays coalesced.  tabs[t][m * 280 + j] belongs to position j * 9 + m (d4w_fft_plan_table_order).
-static __global__ void __launch_bounds__(256, 2)
+constexpr int kPfaThreads = 320;      // 280 / 315 butterflies of the radix-9 / radix-8 stages in one round, <= 102 registers
+static __global__ void __launch_bounds__(kPfaThreads, 2)
 k_xcorr_pfa(XcorrParams xp, const int* __restrict__ tpos, const float* __restrict__ x, const float2* __restrict__ tabs,
             const double* __restrict__ stats, const double* __restrict__ segpre, const double* __restrict__ mu_over_m,
             float* __restrict__ out, size_t out_tpl_stride) {

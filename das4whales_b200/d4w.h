@@ -203,6 +203,8 @@ int d4w_peaks_fill(const unsigned char* dev_flags, int nx, int ns, const int* de
  *      border 0 = BORDER_REFLECT_101 (cv2), 1 = zeros (scipy.signal.correlate(mode='same') of detect.nxcorr2d, detect.py:573);
  *      and binning(mask, 10, 10) + apply_smooth_mask (:166-169, improcess.py:452): out = trace * (resize(mask) != 0). */
 int d4w_scale_pixels(const float* dev_x, float* dev_y, size_t n, float mul, void* dev_ws8, void* stream);
+/* dsp.get_spectrogram's level scaling (dsp.py:76): y = 20 log10(x / max(x)) */
+int d4w_db_re_max(const float* dev_x, float* dev_y, size_t n, void* dev_ws8, void* stream);
 int d4w_resize_aa(const float* dev_in, int ih, int iw, float* dev_out, int oh, int ow, float* dev_tmp, void* stream);
 int d4w_filter2d(const float* dev_in, int h, int w, const float* dev_K, int kh, int kw, float in_thr, float out_thr, int border,
                  float* dev_out, void* stream);

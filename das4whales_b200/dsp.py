@@ -285,7 +285,11 @@ def get_spectrogram(waveform, fs, nfft=128, overlap_pct=0.8):
     xd = _to_device(np.asarray(waveform)[None, :] if not _is_tensor(waveform) else waveform.reshape(1, -1))
     mag = _rows.stft_mag(xd, nfft, hop)[0]             # [1 + nfft/2, frames]
     torch = _fk._torch()
-    p = 20 * torch.log10(mag / mag.max())
+    p = torch.empty_like(mag)
+    ws = torch.empty(2, dtype=torch.int32, device=mag.device)
+    with torch.cuda.device(mag.device.index):          # 20 log10(S / max S) on the device (d4w_db_re_max)
+        _lib.check(_lib.lib().d4w_db_re_max(_lib.ptr(mag, "float*"), _lib.ptr(p, "float*"), mag.numel(), _lib.ptr(ws), _lib.stream_ptr()),
+                   "get_spectrogram")
     height, width = p.shape
     tt = np.linspace(0, xd.shape[1] / fs, num=width)
     ff = np.linspace(0, fs / 2, num=height)
@@ -317,6 +321,30 @@ def snr_tr_array(trace, env=False):
     xd = _to_device(trace)
     y = _rows.snr(xd, env=bool(env))
     return y if _is_tensor(trace) else _to_host64(y)
+
+
+def supported_shape(nx, ns):
+    """Largest (nx', ns') <= (nx, ns) the f-k / row FFT planner accepts.  The GPU transforms are mixed-radix: every prime factor
+    must be <= 61, the time axis must split as ns = T1 * T2 with T1 <= 25 and T2 <= 10 240, and one channel column must fit an
+    SM's shared memory (about 28 000 channels).  numpy.fft takes any length; crop (or pad the record before loading) to the
+    suggested shape when `fk_filter_filt` / `envelope` raise ValueError for an unsupported length."""
+    def smooth(n):
+        for p in (2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31, 37, 41, 43, 47, 53, 59, 61):
+            while n % p == 0:
+                n //= p
+        return n == 1
+
+    def time_ok(n):
+        if not smooth(n):
+            return False
+        return any(n % t1 == 0 and n // t1 <= (16384 if t1 == 1 else 10240) for t1 in (1, 2, 3, 4, 5, 6, 8, 10, 12, 15, 16, 20, 25))
+    nx2 = min(int(nx), 28000)
+    while nx2 > 1 and not smooth(nx2):
+        nx2 -= 1
+    ns2 = int(ns)
+    while ns2 > 1 and not time_ok(ns2):
+        ns2 -= 1
+    return nx2, ns2
 
 
 # north-star aliases
