@@ -515,6 +515,11 @@ def main():
             barrier()
             s_steps = min(steps, 4)
             sh_ms = time_loop(lambda: sflt(xl), s_steps)
+            stage_ms = {}
+            for _ in range(2):
+                sflt(xl, timers=stage_ms)
+            stage_ms = {k: round(v / 2, 3) for k, v in stage_ms.items()}
+            a2a_ms = sum(v for k, v in stage_ms.items() if k.startswith("a2a"))
             # exchange volume per rank and direction: two real-matrix transposes + two pruned-spectrum transposes
             cpr, slab = SHARD_NX // world, SHARD_NS // world
             real_b = cpr * slab * 4 * (world - 1)
@@ -523,7 +528,11 @@ def main():
                                    "(fan mask) with 4 NCCL all-to-all transposes (das4whales_b200.dist.ShardedFkFilter)",
                        "value": SHARD_NX / (sh_ms * 1e-3), "unit": "channels/s", "ms_per_step": sh_ms, "steps": s_steps,
                        "rows_kept": be.rows, "nvlink_bytes_sent_per_rank_per_step": 2 * real_b + 2 * spec_b,
-                       "nvlink_gbs_per_rank_if_exchange_only": round((2 * real_b + 2 * spec_b) / (sh_ms * 1e-3) / 1e9, 1)}
+                       "stage_ms_rank0": stage_ms, "all_to_all_ms": round(a2a_ms, 3),
+                       "compute_and_permute_ms": round(sum(stage_ms.values()) - a2a_ms, 3),
+                       "nvlink_gbs_per_rank_during_exchanges": round((2 * real_b + 2 * spec_b) / max(a2a_ms, 1e-6) / 1e6, 1),
+                       "note": "exchanges are torch.distributed.all_to_all_single (NCCL over NVLink), not yet overlapped with the "
+                               "kernels; SURVEY 8(d) bound: 2 x 3.6 GB per GPU per direction at 900 GB/s = 8 ms"}
             del sflt, be, xl, smask
         except Exception as exc:            # noqa: BLE001
             sharded = {"unavailable": repr(exc)[:300]}

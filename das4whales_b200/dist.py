@@ -143,14 +143,33 @@ class ShardedFkFilter:
         self.dist.all_to_all_single(out, send, output_split_sizes=out_split, input_split_sizes=in_split, group=self.group)
         return out
 
-    def __call__(self, x_local, tapering=False):
-        """x_local: [nx/G, ns] float32 (this rank's channels). Returns the filtered [nx/G, ns]."""
-        recv = self._a2a(*self.stage0_pack_x(x_local))
-        recv = self._a2a(*self.stage1_col_fwd(recv, tapering))
-        send, i_s, o_s = self.stage2_row_filter(recv)
-        self._a2a(send, i_s, o_s, out=self.stage3_recv_buffer())
-        recv = self._a2a(*self.stage3_col_inv())
-        return self.stage4_unpack_y(recv)
+    def __call__(self, x_local, tapering=False, timers=None):
+        """x_local: [nx/G, ns] float32 (this rank's channels). Returns the filtered [nx/G, ns].
+        timers: optional dict; device milliseconds per stage are ADDED to it (CUDA events; one synchronize at the end)."""
+        marks = []
+
+        def mark(name):
+            if timers is not None:
+                import torch
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                marks.append((name, e))
+        mark("start")
+        send = self.stage0_pack_x(x_local); mark("pack_x")
+        recv = self._a2a(*send); mark("a2a_x_to_slabs")
+        send = self.stage1_col_fwd(recv, tapering); mark("col_fwd")
+        recv = self._a2a(*send); mark("a2a_w_to_rows")
+        send, i_s, o_s = self.stage2_row_filter(recv); mark("row_filter_and_permutes")
+        self._a2a(send, i_s, o_s, out=self.stage3_recv_buffer()); mark("a2a_w_to_slabs")
+        send = self.stage3_col_inv(); mark("col_inv")
+        recv = self._a2a(*send); mark("a2a_y_to_channels")
+        y = self.stage4_unpack_y(recv); mark("unpack_y")
+        if timers is not None:
+            import torch
+            torch.cuda.synchronize()
+            for (_, a), (name, b) in zip(marks[:-1], marks[1:]):
+                timers[name] = timers.get(name, 0.0) + a.elapsed_time(b)
+        return y
 
 
 def _exchange(sends, in_splits, out_bufs=None):
