@@ -538,15 +538,6 @@ template <bool PIPE> D4W_HD void stc(cpd* p, cpd z, unsigned long long pol) {
     st16<PIPE>(p, make_float4(f2x_lo(z.x), f2x_hi(z.x), f2x_lo(z.y), f2x_hi(z.y)), pol);
 }
 
-// true if the predicate holds for any active lane of the warp (host emulation: the thread's own predicate)
-D4W_HD bool warp_any(bool p) {
-#ifdef __CUDA_ARCH__
-    return __any_sync(__activemask(), p) != 0;
-#else
-    return p;
-#endif
-}
-
 struct Col2Entry { int pos, slot, flags, pad; };     // flags bit0: conjugate, bit1: stored by the forward pass
 
 template <int X1, bool PIPE = false>
@@ -712,14 +703,9 @@ __host__ __device__ inline void body_colB_fwd_fused(const Col2Params& cp, const 
         static_for<RB>([&](auto ic) {
             constexpr int i = decltype(ic)::value;
             const int2 e = nd[m + RA * i];
-            // most outputs are pruned (6 of 20 kept for the fan mask) and the kept set is nearly the same for every group m of
-            // a warp: skip the whole store block (address arithmetic, repacking, two predicated stores) with one
-            // warp-uniform branch instead of issuing it under false predicates
-            if (warp_any((e.x >= 0) | (e.y >= 0))) {
-                const cpd z = v[outpos<RB>(i)];
-                if (e.x >= 0) st16<PIPE>(wo + (size_t)e.x * ldw, make_float4(f2x_lo(z.x), f2x_lo(z.y), f2x_hi(z.x), f2x_hi(z.y)), pol.stream);
-                if (e.y >= 0) st16<PIPE>(wo + (size_t)e.y * ldw, make_float4(f2x_lo(z.x), -f2x_lo(z.y), f2x_hi(z.x), -f2x_hi(z.y)), pol.stream);
-            }
+            const cpd z = v[outpos<RB>(i)];
+            if (e.x >= 0) st16<PIPE>(wo + (size_t)e.x * ldw, make_float4(f2x_lo(z.x), f2x_lo(z.y), f2x_hi(z.x), f2x_hi(z.y)), pol.stream);
+            if (e.y >= 0) st16<PIPE>(wo + (size_t)e.y * ldw, make_float4(f2x_lo(z.x), -f2x_lo(z.y), f2x_hi(z.x), -f2x_hi(z.y)), pol.stream);
         });
     }
 }
@@ -741,13 +727,10 @@ __host__ __device__ inline void body_colB_inv_fused(const Col2Params& cp, cpd* _
             const int2 e = nd[m + RA * i];
             const int sd = e.x, sm = (e.y >= 0) ? e.y : ((e.y <= -2) ? -2 - e.y : -1);
             const int sl = sd >= 0 ? sd : sm;                           // one predicated load, sign applied afterwards
-            v[i] = dmake(vbc(0.f), vbc(0.f));
-            if (warp_any(ok && sl >= 0)) {                              // pruned inputs: one warp-uniform branch, nothing else
-                const float sg = sd >= 0 ? 1.f : -1.f;
-                float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (ok && sl >= 0) u = ld16<PIPE>(wi + (size_t)sl * ldw, pol.stream);
-                v[i] = dmake(f2x_set(u.x, u.z), f2x_set(sg * u.y, sg * u.w));
-            }
+            const float sg = sd >= 0 ? 1.f : -1.f;
+            float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ok && sl >= 0) u = ld16<PIPE>(wi + (size_t)sl * ldw, pol.stream);
+            v[i] = dmake(f2x_set(u.x, u.z), f2x_set(sg * u.y, sg * u.w));
         });
         DFTD<RB, true>::run(v);
         cpd* dst = smem + j * fs + RB * m;
