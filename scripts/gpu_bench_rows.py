@@ -67,3 +67,22 @@ img = dw.improcess.binning(dw.improcess.trace2image(x), 1 / 10, 1 / 10)
 up, down = dw.improcess.gabor_filt_design(74.77)
 report("filter2D 101x101 on the binned image", timeit(lambda: dw.improcess.filter2D(img, None, up + down)), 8 * img.numel(),
        "%d x %d image, %.2f GFMA" % (img.shape[0], img.shape[1], img.numel() * 10201 / 1e9))
+# ---- the whole device-side pipeline of one file (no H2D) -------------------------------------------------------------------
+from das4whales_b200 import pipeline
+raw = (x * 5.0e4).round().to(torch.int32)
+pipe = pipeline.MfDetectPipeline(NX, NS, [0, NX, 1], DX, FS, 1e-9)
+pipe.process_device(raw); torch.cuda.synchronize()
+import time as _t
+t0 = _t.perf_counter()
+for _ in range(3):
+    res = pipe.process_device(raw)
+torch.cuda.synchronize()
+report("pipeline.process_device (raw2strain .. picks, data resident)", (_t.perf_counter() - t0) / 3 * 1e3, 4 * S,
+       "%d + %d picks" % (res["picks_hf"][1].numel(), res["picks_lf"][1].numel()))
+pipe2 = pipeline.MfDetectPipeline(NX, NS, [0, NX, 1], DX, FS, 1e-9, prune_eps=1e-5)
+pipe2.process_device(raw); torch.cuda.synchronize()
+t0 = _t.perf_counter()
+for _ in range(3):
+    res = pipe2.process_device(raw)
+torch.cuda.synchronize()
+report("pipeline.process_device, f-k mask pruned at eps = 1e-5", (_t.perf_counter() - t0) / 3 * 1e3, 4 * S)
