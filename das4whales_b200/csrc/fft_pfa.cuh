@@ -101,9 +101,11 @@ __host__ __device__ inline void pfa_last_fused(const cpd* __restrict__ S, cpd* _
     constexpr int R = 9, G = kPfaN / R;
     for (int j = tid; j < G; j += nthr) {
         cpd v[R], u[R];
+        float2 tb[R];                                   // table loads first: their L2 latency hides under the forward butterfly
+        static_for<R>([&](auto mc) { constexpr int m = decltype(mc)::value; tb[m] = tab[m * G + j]; });
         static_for<R>([&](auto qc) { constexpr int q = decltype(qc)::value; v[q] = S[j * R + q]; });
         DFTD<R, false>::run(v);
-        static_for<R>([&](auto mc) { constexpr int m = decltype(mc)::value; u[m] = dmul_s(v[outpos<R>(m)], tab[m * G + j]); });
+        static_for<R>([&](auto mc) { constexpr int m = decltype(mc)::value; u[m] = dmul_s(v[outpos<R>(m)], tb[m]); });
         DFTD<R, true>::run(u);
         static_for<R>([&](auto qc) { constexpr int q = decltype(qc)::value; B[j * R + q] = u[outpos<R>(q)]; });
     }
