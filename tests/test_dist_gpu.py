@@ -34,14 +34,16 @@ def _mask(dw, kind, nx, ns):
     return dw.dsp.hybrid_ninf_filter_design((nx, ns), [0, nx, 1], DX, FS, 1350., 1450., 3300, 3450, 14., 30.)
 
 
-@pytest.mark.parametrize("nx,ns,world,kind,taper", [
-    (1000, 4800, 2, "fan", False),        # 25 x 40: two-level, engine level B, separate launches
-    (10000, 4800, 2, "fan", True),        # 25 x 400: the pipelined kernels of the headline configuration, on 2400-sample slabs
-    (10000, 4800, 4, "hybrid", False),    # nothing pruned, 4 ranks, uneven row split (5001 rows)
-    (600, 3600, 3, "fan", False),         # 3 ranks
-    (20000, 1920, 4, "fan", False),       # config-4 channel count (25 x 800): two-level with the three-stage level B
+@pytest.mark.parametrize("nx,ns,world,kind,taper,nsub", [
+    (1000, 4800, 2, "fan", False, 1),        # 25 x 40: two-level, engine level B, separate launches
+    (10000, 4800, 2, "fan", True, 1),        # 25 x 400: the pipelined kernels of the headline configuration, on 2400-sample slabs
+    (10000, 4800, 4, "hybrid", False, 1),    # nothing pruned, 4 ranks, uneven row split (5001 rows)
+    (600, 3600, 3, "fan", False, 1),         # 3 ranks
+    (20000, 1920, 4, "fan", False, 1),       # config-4 channel count (25 x 800): two-level with the three-stage level B
+    (10000, 9600, 2, "fan", True, 3),        # three sub-slabs of 1600 samples per rank (the overlapped schedule's slicing)
+    (20000, 3840, 4, "fan", False, 2),       # config-4 channel count, two sub-slabs
 ])
-def test_sharded_cuda_backend_local_group(dw, nx, ns, world, kind, taper):
+def test_sharded_cuda_backend_local_group(dw, nx, ns, world, kind, taper, nsub):
     import torch
     from das4whales_b200 import dist as d4wdist
     from das4whales_b200.fk import FkFilter
@@ -49,7 +51,7 @@ def test_sharded_cuda_backend_local_group(dw, nx, ns, world, kind, taper):
     x = torch.randn((nx, ns), device="cuda", generator=gen)
     mask = _mask(dw, kind, nx, ns)
     ref = FkFilter(mask)(x, tapering=taper)                       # single-GPU path (checked against the oracle elsewhere)
-    be = d4wdist.CudaBackend(mask, nx, ns, world)
+    be = d4wdist.CudaBackend(mask, nx, ns, world, nsub=nsub)
     filters = [d4wdist.ShardedFkFilter(nx, ns, be, rank=r, world=world) for r in range(world)]
     cpr = nx // world
     ys = d4wdist.run_local_group(filters, [x[r * cpr:(r + 1) * cpr].contiguous() for r in range(world)], tapering=taper)
@@ -80,9 +82,11 @@ def _nccl_worker(rank, world, port, nx, ns, q):
     mask = dw.dsp.fk_filter_design((nx, ns), [0, nx, 1], DX, FS)
     ref = FkFilter(mask)(x)
     cpr = nx // world
-    y = d4wdist.fk_filter_filt_sharded(x[rank * cpr:(rank + 1) * cpr].contiguous(), mask, nx)
     r = ref[rank * cpr:(rank + 1) * cpr]
-    err = float((y - r).abs().max() / ref.abs().max())
+    err = 0.0
+    for nsub in (1, 3):                                            # serial schedule and the overlapped one (async all-to-alls)
+        y = d4wdist.fk_filter_filt_sharded(x[rank * cpr:(rank + 1) * cpr].contiguous(), mask, nx, nsub=nsub)
+        err = max(err, float((y - r).abs().max() / ref.abs().max()))
     q.put((rank, err))
     dist.destroy_process_group()
 
