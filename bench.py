@@ -42,8 +42,8 @@ SHARD_NX, SHARD_NS = 20000, 240000  # BASELINE configs[3]
 
 # ncu --set full dram__bytes_read.sum + dram__bytes_write.sum per launch, keyed by what was profiled: (column scheme,
 # kept rows).  Used only when the plan that runs equals the profiled one; otherwise `traffic` is null.
-NCU_TRAFFIC = {(3, 1356): {"step": 7.34e9 + 2.60e9 + 3.27e9 + 2.60e9 + 8.04e9, "p5": 8.04e9,
-                           "src": "profiles/r01d_fk_pipe.txt (P1 7.34, P3 3.27 (r01c), P5 8.04 GB; P2/P4 2.60 GB each)"}}
+NCU_TRAFFIC = {(3, 1356): {"step": 7.390e9 + 2.547e9 + 3.256e9 + 2.546e9 + 8.044e9, "p5": 8.044e9,
+                           "src": "profiles/r02_fk_pipe.txt (P1 7.390, P2 2.547, P3 3.256, P4 2.546, P5 8.044 GB)"}}
 COL_KERNEL = {0: "k_col_inv_dual", 1: "k_col_inv_tma", 2: "k_colB_inv_fused + k_colA_inv", 3: "k_col2_pipe<inverse>"}
 
 
