@@ -183,7 +183,7 @@ extern "C" int d4w_fk_plan_create(d4w_fk_plan** out, int nx, int ns, int device)
             PipeParams& pp = pl->pipe;
             pp.nchunks = (ns / 2 + hp.chunk_pairs - 1) / hp.chunk_pairs;
             pp.lag = hp.pipe_lag; pp.nbuf = hp.pipe_lag + std::max(2, env_int("D4W_PIPE_SLACK", 2));
-            pp.cq = hp.pipe_cq; pp.rpc = 160 / hp.pipe_cq;
+            pp.cq = hp.pipe_cq; pp.rpc = (hp.fused3 ? hp.colb_threads : 160) / hp.pipe_cq;
             pp.nA = (hp.x2 + pp.rpc - 1) / pp.rpc;
             pp.tiles = hp.chunk_pairs / hp.np2; pp.nB = hp.planes * pp.tiles;
             pp.hints = env_int("D4W_PIPE_HINTS", 1);
@@ -271,7 +271,7 @@ static int mask_finish_support(d4w_fk_mask* m, void* stream_v, double eps_arg = 
         for (size_t i = 0; i < ents.size(); ++i) dev[i] = Col2Entry{ents[i].pos, ents[i].slot, ents[i].flags, 0};
         D4W_CUDA_TRY(upload(&m->d_plane_ptr, plane_ptr));
         D4W_CUDA_TRY(upload(&m->d_ents, dev));
-        if (pl->hostplan.fused_ra) {
+        if (pl->hostplan.fused_ra || pl->hostplan.fused3) {
             std::vector<int2> need;
             build_col2_need(pl->hostplan, k2slot, need);
             D4W_CUDA_TRY(upload(&m->d_need, need));
@@ -445,6 +445,33 @@ static int launch_col2_pipe(const d4w_fk_plan* pl, const d4w_fk_mask* m, const f
     const unsigned grid = (unsigned)(pp.nchunks + pp.lag) * (unsigned)(pp.nA + pp.nB);
     const int ra = pl->hostplan.fused_ra, x1 = pl->col2.x1;
     bool done = false;
+    if (pl->hostplan.fused3) {
+        const int* r3 = pl->hostplan.r3;
+        const int occ3 = env_int("D4W_PIPE3_OCC", 3);
+#define D4W_PIPE3(R0, R1, R2, OCC)                                                                                        \
+        if (!done && r3[0] == R0 && r3[1] == R1 && r3[2] == R2 && occ3 == OCC) {                                          \
+            static bool attr_done_dev[64] = {};                                                                           \
+            bool& attr_done = attr_done_dev[pl->device & 63];                                                             \
+            if (!attr_done) { cudaFuncSetAttribute(k_col3_pipe<10, R0, R1, R2, INV, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_done = true; } \
+            k_col3_pipe<10, R0, R1, R2, INV, OCC><<<grid, pl->colb_threads, smem, stream>>>(pl->col2, pp, x, y, v2, w, ldw, m->d_need, tap); \
+            done = true;                                                                                                  \
+        }
+        D4W_PIPE3(10, 10, 10, 3) D4W_PIPE3(10, 10, 10, 4) D4W_PIPE3(10, 10, 10, 2) D4W_PIPE3(5, 5, 4, 3)
+#undef D4W_PIPE3
+        if (!done) return fail(D4W_ERR_UNSUPPORTED, "three-stage pipelined column kernel: unsupported split / occupancy");
+        D4W_CHECK_LAUNCH("k_col3_pipe");
+        return D4W_OK;
+    }
+    const int occ = env_int("D4W_PIPE_OCC", 3);       // CTAs per SM the kernel is compiled for: 3 = 128 registers (default), 4 = 96 (spills), 2 = 200
+#define D4W_PIPE_OCC(X1, RA, RB, OCC)                                                                                     \
+    if (!done && x1 == X1 && ra == RA && occ == OCC) {                                                                    \
+        static bool attr_done_dev[64] = {};                                                                               \
+        bool& attr_done = attr_done_dev[pl->device & 63];                                                                 \
+        if (!attr_done) { cudaFuncSetAttribute(k_col2_pipe<X1, RA, RB, INV, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_done = true; } \
+        k_col2_pipe<X1, RA, RB, INV, OCC><<<grid, 160, smem, stream>>>(pl->col2, pp, x, y, v2, w, ldw, m->d_need, tap);   \
+        done = true;                                                                                                      \
+    }
+    D4W_PIPE_OCC(25, 20, 20, 4) D4W_PIPE_OCC(25, 20, 20, 2)
 #define D4W_PIPE(X1, RA, RB)                                                                                              \
     if (!done && x1 == X1 && ra == RA) {                                                                                  \
         static bool attr_done_dev[64] = {};                                                                               \
@@ -454,6 +481,7 @@ static int launch_col2_pipe(const d4w_fk_plan* pl, const d4w_fk_mask* m, const f
         done = true;                                                                                                      \
     }
     D4W_PIPE(25, 20, 20) D4W_PIPE(25, 16, 25) D4W_PIPE(20, 20, 20) D4W_PIPE(20, 16, 25) D4W_PIPE(16, 20, 20) D4W_PIPE(16, 16, 25)
+#undef D4W_PIPE_OCC
 #undef D4W_PIPE
     if (!done) return fail(D4W_ERR_UNSUPPORTED, "pipelined column kernel: unsupported split");
     D4W_CHECK_LAUNCH("k_col2_pipe");

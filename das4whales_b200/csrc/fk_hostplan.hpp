@@ -23,6 +23,7 @@ struct FkHostPlan {
     int pipe = 0, pipe_lag = 2, pipe_cq = 80;   // single-launch pipelined level A+B (V ring resident in L2)
     int chunk_pairs = 0;              // sample pairs per level-A/level-B launch pair (V chunk sized to stay in L2)
     int fused_ra = 0, fused_rb = 0;   // level B as a fused two-stage transform (X2 = ra * rb) when both radices are in {16, 20, 25}
+    int fused3 = 0, r3[3] = {0, 0, 0};   // X1 = 10 with a three-stage small-radix level B (k_col3_pipe), opt-in: D4W_COL_PIPE3=1
     FftPlan colpl{}, rowpl{};
     std::vector<float2> tw_col, tw_row, twT;
     std::vector<int> pos2k, k2pos, pos2k_row;
@@ -131,8 +132,35 @@ inline int build_fk_hostplan(int nx, int ns, size_t smem_cap, FkHostPlan& hp, st
               " has no supported split (needs ns = T1*T2 with T1 <= 25, T2 <= 6144 (10240 scalar) and prime factors <= 61)";
         return 1;
     }
+    // ---- small-radix variant: X1 = 10 in registers, X2 = R0*R1*R2 with radices <= 10 (three-stage level B), single pipelined launch
+    if (env_int("D4W_COL_TWO_LEVEL", 1) && env_int("D4W_COL_PIPE3", 0) && ns % 4 == 0 && nx % 10 == 0) {
+        const int x2 = nx / 10;
+        static const int cand[][3] = {{10, 10, 10}, {5, 5, 4}};
+        for (auto& c : cand) {
+            if (c[0] * c[1] * c[2] != x2) continue;
+            FftPlan tmp;
+            const std::string spec = std::to_string(c[0]) + "," + std::to_string(c[1]) + "," + std::to_string(c[2]);
+            if (!make_plan_from_string(x2, spec.c_str(), tmp)) continue;
+            int np = env_int("D4W_PIPE3_NP", 4);
+            if (np != 1 && np != 2 && np != 4 && np != 8) np = 4;
+            int threads = env_int("D4W_PIPE3_THREADS", 200);
+            int cq = env_int("D4W_PIPE3_CQ", 50);
+            if (threads < 32 || threads > 224 || cq < 2 || threads % cq || (2 * cq) % np) { threads = 200; cq = 50; np = 4; }
+            hp.two_level = 1; hp.x1 = 10; hp.x2 = x2; hp.planes = 6; hp.np2 = np; hp.fstride2 = x2 | 1;
+            hp.plb = tmp; hp.colb_smem = (size_t)np * hp.fstride2 * 16;
+            hp.fused3 = 1; hp.r3[0] = c[0]; hp.r3[1] = c[1]; hp.r3[2] = c[2];
+            hp.pipe = 1; hp.pipe_cq = cq; hp.chunk_pairs = std::min(2 * cq, ns / 2);
+            hp.pipe_lag = std::min(256, std::max(1, env_int("D4W_PIPE_LAG", 2)));
+            hp.colb_threads = threads;
+            hp.tw_x2 = make_twiddles(x2);
+            auto p2k = make_pos2freq(tmp);
+            hp.pos_x2.assign((size_t)x2, 0);
+            for (int p = 0; p < x2; ++p) hp.pos_x2[p2k[p]] = p;
+            break;
+        }
+    }
     // ---- two-level column split: X1 in registers (largest of 25, 20, 16), X2-point smem FFT
-    if (env_int("D4W_COL_TWO_LEVEL", 1) && ns % 4 == 0) {
+    if (!hp.fused3 && env_int("D4W_COL_TWO_LEVEL", 1) && ns % 4 == 0) {
         const int forced_x1 = env_int("D4W_COL_X1", 0);
         for (int cand : {25, 20, 16}) {
             if (forced_x1 && cand != forced_x1) continue;

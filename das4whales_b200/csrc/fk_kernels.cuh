@@ -751,6 +751,119 @@ __host__ __device__ inline void body_colB_inv_fused(const Col2Params& cp, cpd* _
 }
 
 
+// ------------------------------------------------------------------ three-stage level B (X2 = R0 * R1 * R2, small radices)
+// Same contract as the fused two-stage version (stage 0 from global memory, last stage to the kept rows), with one more
+// in-place shared-memory stage in between.  Radices <= 10 keep every butterfly under ~45 data registers, so the pipelined
+// kernel built on it (k_col3_pipe, X1 = 10) needs ~70 registers instead of 128 and 21 - 28 warps share an SM instead of 15:
+// the round-1 / round-2 profiles show the column kernels bound by latency at low occupancy, not by any one unit.
+// Positions follow the engine's decimation in frequency: after the forward stages position m0*L0 + m1*L1 + m2 holds
+// k2 = m0 + R0*m1 + R0*R1*m2 (L0 = X2/R0, L1 = R2).
+template <int R0, int R1, int R2, bool PIPE = false>
+__host__ __device__ inline void body_colB3_fwd(const Col2Params& cp, const cpd* __restrict__ v2, float2* __restrict__ w, size_t ldw,
+                                               const int2* __restrict__ need, int plane, int tile, int tid, int nthr, cpd* smem,
+                                               int tpb, int tpn, L2Pol pol = L2Pol{0, 0}) {
+    constexpr int X2 = R0 * R1 * R2, L0 = X2 / R0, L1 = L0 / R1;
+    const int np = cp.np, sh = cp.np_shift, hp = cp.vhp, fs = cp.fstride;
+    const int tp0 = tile * np;
+    const cpd zero = dmake(vbc(0.f), vbc(0.f));
+    for (int it = tid; it < (L0 << sh); it += nthr) {              // stage 0: item (n, j), inputs c2 = n + L0*q
+        const int n = it >> sh, j = it & (np - 1);
+        const bool ok = tp0 + j < tpn;
+        cpd v[R0];
+        const cpd* src = v2 + ((size_t)plane * X2 + n) * hp + tp0 + j;
+        static_for<R0>([&](auto qc) { constexpr int q = decltype(qc)::value; v[q] = ok ? ldc<PIPE>(src + (size_t)(L0 * q) * hp, pol.keep) : zero; });
+        DFTD<R0, false>::run(v);
+        apply_stage_twiddles<R0, false, true>(v, cp.twb[n]);                       // W_X2^{n m}
+        cpd* dst = smem + j * fs + n;
+        static_for<R0>([&](auto mc) { constexpr int m = decltype(mc)::value; dst[L0 * m] = v[outpos<R0>(m)]; });
+    }
+    D4W_SYNC();
+    for (int it = tid; it < ((R0 * L1) << sh); it += nthr) {        // stage 1: item (b0, n1, j) inside block b0
+        const int idx = it >> sh, j = it & (np - 1);
+        const int b0 = idx / L1, n1 = idx - b0 * L1;
+        cpd* base = smem + j * fs + b0 * L0 + n1;
+        cpd v[R1];
+        static_for<R1>([&](auto qc) { constexpr int q = decltype(qc)::value; v[q] = base[L1 * q]; });
+        DFTD<R1, false>::run(v);
+        apply_stage_twiddles<R1, false, true>(v, cp.twb[R0 * n1]);                  // W_L0^{n1 m} = W_X2^{R0 n1 m}
+        static_for<R1>([&](auto mc) { constexpr int m = decltype(mc)::value; base[L1 * m] = v[outpos<R1>(m)]; });
+    }
+    D4W_SYNC();
+    const int2* nd = need + (size_t)plane * X2;
+    for (int it = tid; it < ((R0 * R1) << sh); it += nthr) {        // stage 2: contiguous group g = b0*R1 + b1 -> kept rows
+        const int g = it >> sh, j = it & (np - 1);
+        if (tp0 + j >= tpn) continue;
+        const int b0 = g / R1, b1 = g - b0 * R1;
+        cpd v[R2];
+        const cpd* src = smem + j * fs + g * R2;
+        static_for<R2>([&](auto ic) { constexpr int i = decltype(ic)::value; v[i] = src[i]; });
+        DFTD<R2, false>::run(v);
+        float2* wo = w + 2 * (size_t)(tpb + tp0 + j);
+        const int k0 = b0 + R0 * b1;
+        static_for<R2>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            const int2 e = nd[k0 + R0 * R1 * i];
+            const cpd z = v[outpos<R2>(i)];
+            if (e.x >= 0) st16<PIPE>(wo + (size_t)e.x * ldw, make_float4(f2x_lo(z.x), f2x_lo(z.y), f2x_hi(z.x), f2x_hi(z.y)), pol.stream);
+            if (e.y >= 0) st16<PIPE>(wo + (size_t)e.y * ldw, make_float4(f2x_lo(z.x), -f2x_lo(z.y), f2x_hi(z.x), -f2x_hi(z.y)), pol.stream);
+        });
+    }
+}
+
+template <int R0, int R1, int R2, bool PIPE = false>
+__host__ __device__ inline void body_colB3_inv(const Col2Params& cp, cpd* __restrict__ v2, const float2* __restrict__ w, size_t ldw,
+                                               const int2* __restrict__ need, int plane, int tile, int tid, int nthr, cpd* smem,
+                                               int tpb, int tpn, L2Pol pol = L2Pol{0, 0}) {
+    constexpr int X2 = R0 * R1 * R2, L0 = X2 / R0, L1 = L0 / R1;
+    const int np = cp.np, sh = cp.np_shift, hp = cp.vhp, fs = cp.fstride;
+    const int tp0 = tile * np;
+    const int2* nd = need + (size_t)plane * X2;
+    for (int it = tid; it < ((R0 * R1) << sh); it += nthr) {        // undo stage 2: gather the kept rows
+        const int g = it >> sh, j = it & (np - 1);
+        const bool ok = tp0 + j < tpn;
+        const int b0 = g / R1, b1 = g - b0 * R1;
+        const int k0 = b0 + R0 * b1;
+        cpd v[R2];
+        const float2* wi = w + 2 * (size_t)(tpb + tp0 + j);
+        static_for<R2>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            const int2 e = nd[k0 + R0 * R1 * i];
+            const int sd = e.x, sm = (e.y >= 0) ? e.y : ((e.y <= -2) ? -2 - e.y : -1);
+            const int sl = sd >= 0 ? sd : sm;
+            const float sg = sd >= 0 ? 1.f : -1.f;
+            float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ok && sl >= 0) u = ld16<PIPE>(wi + (size_t)sl * ldw, pol.stream);
+            v[i] = dmake(f2x_set(u.x, u.z), f2x_set(sg * u.y, sg * u.w));
+        });
+        DFTD<R2, true>::run(v);
+        cpd* dst = smem + j * fs + g * R2;
+        static_for<R2>([&](auto ic) { constexpr int i = decltype(ic)::value; dst[i] = v[outpos<R2>(i)]; });
+    }
+    D4W_SYNC();
+    for (int it = tid; it < ((R0 * L1) << sh); it += nthr) {        // undo stage 1
+        const int idx = it >> sh, j = it & (np - 1);
+        const int b0 = idx / L1, n1 = idx - b0 * L1;
+        cpd* base = smem + j * fs + b0 * L0 + n1;
+        cpd v[R1];
+        static_for<R1>([&](auto mc) { constexpr int m = decltype(mc)::value; v[m] = base[L1 * m]; });
+        apply_stage_twiddles<R1, true, false>(v, cp.twb[R0 * n1]);
+        DFTD<R1, true>::run(v);
+        static_for<R1>([&](auto qc) { constexpr int q = decltype(qc)::value; base[L1 * q] = v[outpos<R1>(q)]; });
+    }
+    D4W_SYNC();
+    for (int it = tid; it < (L0 << sh); it += nthr) {              // undo stage 0 -> plane of V
+        const int n = it >> sh, j = it & (np - 1);
+        if (tp0 + j >= tpn) continue;
+        cpd v[R0];
+        const cpd* src = smem + j * fs + n;
+        static_for<R0>([&](auto mc) { constexpr int m = decltype(mc)::value; v[m] = src[L0 * m]; });
+        apply_stage_twiddles<R0, true, false>(v, cp.twb[n]);
+        DFTD<R0, true>::run(v);
+        cpd* dst = v2 + ((size_t)plane * X2 + n) * hp + tp0 + j;
+        static_for<R0>([&](auto qc) { constexpr int q = decltype(qc)::value; stc<PIPE>(dst + (size_t)(L0 * q) * hp, v[outpos<R0>(q)], pol.keep); });
+    }
+}
+
 // ---- fused row kernel: first stage straight from global memory, last stage . mask . its inverse in registers ----
 // The T2-point piece makes one trip through shared memory per middle stage instead of one per stage plus a mask
 // pass.  Table order for this kernel: tab[m * (n / RL) + j] belongs to position j * RL + m of the engine's order.
@@ -1172,8 +1285,8 @@ __device__ __forceinline__ void pipe_signal(unsigned* p) {
     if (threadIdx.x == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" :: "l"(p) : "memory");
 }
 
-template <int X1, int RA, int RB, bool INV>
-static __global__ void __launch_bounds__(160, 3)
+template <int X1, int RA, int RB, bool INV, int OCC = 3>
+static __global__ void __launch_bounds__(160, OCC)
 k_col2_pipe(Col2Params cp, PipeParams pp, const float* __restrict__ x, float* __restrict__ y, cpd* v2, float2* w, size_t ldw,
             const int2* __restrict__ need, const float* __restrict__ taper) {
     __shared__ unsigned s_ticket;
@@ -1207,6 +1320,49 @@ k_col2_pipe(Col2Params cp, PipeParams pp, const float* __restrict__ x, float* __
         if (tile * cp.np < tpn) {
             if constexpr (!INV) body_colB_fwd_fused<RA, RB, true>(cp, vb, w, ldw, need, plane, tile, threadIdx.x, blockDim.x, reinterpret_cast<cpd*>(d4w_dyn_smem), tpb, tpn, pol);
             else body_colB_inv_fused<RA, RB, true>(cp, vb, w, ldw, need, plane, tile, threadIdx.x, blockDim.x, reinterpret_cast<cpd*>(d4w_dyn_smem), tpb, tpn, pol);
+        }
+        pipe_signal(cntB + c);
+    }
+}
+#endif
+
+#ifdef __CUDACC__
+// pipelined level A (radix X1 in registers) + three-stage level B: same ticket / ring protocol as k_col2_pipe
+template <int X1, int R0, int R1, int R2, bool INV, int OCC>
+static __global__ void __launch_bounds__(224, OCC)
+k_col3_pipe(Col2Params cp, PipeParams pp, const float* __restrict__ x, float* __restrict__ y, cpd* v2, float2* w, size_t ldw,
+            const int2* __restrict__ need, const float* __restrict__ taper) {
+    __shared__ unsigned s_ticket;
+    if (threadIdx.x == 0) s_ticket = atomicAdd(pp.cnt, 1u);
+    __syncthreads();
+    const int per = pp.nA + pp.nB;
+    const int slot = (int)(s_ticket / (unsigned)per), r = (int)(s_ticket % (unsigned)per);
+    const int nfirst = INV ? pp.nB : pp.nA;
+    const bool first = r < nfirst;
+    const int c = first ? slot : slot - pp.lag;
+    if (c < 0 || c >= pp.nchunks) return;
+    const int idx = first ? r : r - nfirst;
+    const bool roleA = first != INV;
+    unsigned* cntA = pp.cnt + 1;
+    unsigned* cntB = pp.cnt + 1 + pp.nchunks;
+    const int tpb = c * cp.vhp, tpn = min(cp.vhp, cp.ns / 2 - tpb);
+    cpd* vb = v2 + (size_t)(c % pp.nbuf) * pp.vbuf_elems;
+    const L2Pol pol = make_l2pol(pp.hints != 0);
+    if (first) { if (c >= pp.nbuf) pipe_wait((INV ? cntA : cntB) + (c - pp.nbuf), (unsigned)(INV ? pp.nA : pp.nB)); }
+    else pipe_wait((INV ? cntB : cntA) + c, (unsigned)(INV ? pp.nB : pp.nA));
+    if (roleA) {
+        const int row = (int)threadIdx.x / pp.cq, q = (int)threadIdx.x - row * pp.cq;
+        const int c2 = idx * pp.rpc + row;
+        if (row < pp.rpc && c2 < cp.x2 && q < tpn / 2) {
+            if constexpr (!INV) body_colA_fwd<X1, true>(cp, x, vb, taper, c2, q, tpb, pol);
+            else body_colA_inv<X1, true>(cp, vb, y, c2, q, tpb, pol);
+        }
+        pipe_signal(cntA + c);
+    } else {
+        const int plane = idx / pp.tiles, tile = idx - plane * pp.tiles;
+        if (tile * cp.np < tpn) {
+            if constexpr (!INV) body_colB3_fwd<R0, R1, R2, true>(cp, vb, w, ldw, need, plane, tile, threadIdx.x, blockDim.x, reinterpret_cast<cpd*>(d4w_dyn_smem), tpb, tpn, pol);
+            else body_colB3_inv<R0, R1, R2, true>(cp, vb, w, ldw, need, plane, tile, threadIdx.x, blockDim.x, reinterpret_cast<cpd*>(d4w_dyn_smem), tpb, tpn, pol);
         }
         pipe_signal(cntB + c);
     }

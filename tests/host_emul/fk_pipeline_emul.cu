@@ -30,6 +30,7 @@ static void colA_dispatch(bool inv, const Col2Params& c2p, const float* x, cpd* 
     switch (c2p.x1) {
         case 25: colA_all<25>(inv, c2p, x, v2, y, taper); break;
         case 20: colA_all<20>(inv, c2p, x, v2, y, taper); break;
+        case 10: colA_all<10>(inv, c2p, x, v2, y, taper); break;
         default: colA_all<16>(inv, c2p, x, v2, y, taper); break;
     }
 }
@@ -44,6 +45,14 @@ static void split_dispatch(int t1, bool inv, float2* w, size_t ldw, int t2, cons
 
 template <bool INV>
 static bool colB_fused_emul(const FkHostPlan& hp, const Col2Params& c2p, cpd* v2, float2* w, size_t ldw, const int2* need, int pl, int tb, cpd* smem) {
+#define EM_FUSED3(R0, R1, R2)                                                                                \
+    if (hp.fused3 && hp.r3[0] == R0 && hp.r3[1] == R1 && hp.r3[2] == R2) {                                   \
+        if constexpr (!INV) body_colB3_fwd<R0, R1, R2>(c2p, v2, w, ldw, need, pl, tb, 0, 1, smem, c2p.tpb, c2p.tpn);           \
+        else body_colB3_inv<R0, R1, R2>(c2p, v2, w, ldw, need, pl, tb, 0, 1, smem, c2p.tpb, c2p.tpn);                          \
+        return true;                                                                                         \
+    }
+    EM_FUSED3(10, 10, 10) EM_FUSED3(5, 5, 4)
+#undef EM_FUSED3
 #define EM_FUSED(RA, RB)                                                                                     \
     if (hp.fused_ra == RA && hp.fused_rb == RB) {                                                            \
         if constexpr (!INV) body_colB_fwd_fused<RA, RB>(c2p, v2, w, ldw, need, pl, tb, 0, 1, smem, c2p.tpb, c2p.tpn);          \
@@ -106,14 +115,14 @@ int main(int argc, char** argv) {
         std::vector<Col2EntryHost> eh; build_col2_entries(hp, k2slot, plane_ptr, eh);
         for (auto& e : eh) ents2.push_back(Col2Entry{e.pos, e.slot, e.flags, 0});
         smem.resize(std::max(smem.size(), hp.colb_smem / sizeof(float2) + 16));
-        if (hp.fused_ra) build_col2_need(hp, k2slot, need2);
+        if (hp.fused_ra || hp.fused3) build_col2_need(hp, k2slot, need2);
         for (int tpb = 0; tpb < ns / 2; tpb += hp.chunk_pairs) {
             c2p.tpb = tpb; c2p.tpn = std::min(hp.chunk_pairs, ns / 2 - tpb);
             colA_dispatch(false, c2p, x.data(), v2.data(), nullptr, taper ? hp.taper.data() : nullptr);
             const int ntb = (c2p.tpn + hp.np2 - 1) / hp.np2;
             for (int pl = 0; pl < hp.planes; ++pl)
                 for (int tb = 0; tb < ntb; ++tb)
-                    if (!(hp.fused_ra && colB_fused_emul<false>(hp, c2p, v2.data(), w.data(), ldw, need2.data(), pl, tb, reinterpret_cast<cpd*>(smem.data()))))
+                    if (!((hp.fused_ra || hp.fused3) && colB_fused_emul<false>(hp, c2p, v2.data(), w.data(), ldw, need2.data(), pl, tb, reinterpret_cast<cpd*>(smem.data()))))
                         body_colB_fwd(c2p, v2.data(), w.data(), ldw, plane_ptr.data(), ents2.data(), pl, tb, 0, 1, reinterpret_cast<cpd*>(smem.data()));
         }
     }
@@ -141,7 +150,7 @@ int main(int argc, char** argv) {
             const int ntb = (c2p.tpn + hp.np2 - 1) / hp.np2;
             for (int pl = 0; pl < hp.planes; ++pl)
                 for (int tb = 0; tb < ntb; ++tb)
-                    if (!(hp.fused_ra && colB_fused_emul<true>(hp, c2p, v2.data(), w.data(), ldw, need2.data(), pl, tb, reinterpret_cast<cpd*>(smem.data()))))
+                    if (!((hp.fused_ra || hp.fused3) && colB_fused_emul<true>(hp, c2p, v2.data(), w.data(), ldw, need2.data(), pl, tb, reinterpret_cast<cpd*>(smem.data()))))
                         body_colB_inv(c2p, v2.data(), w.data(), ldw, plane_ptr.data(), ents2.data(), pl, tb, 0, 1, reinterpret_cast<cpd*>(smem.data()));
             colA_dispatch(true, c2p, nullptr, v2.data(), y.data(), nullptr);
         }

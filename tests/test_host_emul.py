@@ -73,7 +73,9 @@ CASES = [(40, 240, 1, False, None), (45, 175, 1, True, None), (38, 120, 2, False
          (6400, 36, 1, True, {"D4W_COL_X1": "16", "D4W_COL_CHUNK_PAIRS": "8", "D4W_COLB_FUSED": "0"}),
          (6400, 12, 1, False, {"D4W_COL_X1": "16"}), (8000, 8, 1, True, {"D4W_COL_X1": "20"}),
          (10000, 8, 1, False, {"D4W_COL_TWO_LEVEL": "0"}),   # single-level dual column kernels (20x20x25)
-         (400, 24, 1, True, None), (320, 12, 1, True, {"D4W_COL_X1": "16"}), (500, 16, 1, False, {"D4W_COL_X1": "20"})]
+         (400, 24, 1, True, None), (320, 12, 1, True, {"D4W_COL_X1": "16"}), (500, 16, 1, False, {"D4W_COL_X1": "20"}),
+         (10000, 16, 1, True, {"D4W_COL_PIPE3": "1"}),        # X1 = 10, three-stage 10 x 10 x 10 level B (k_col3_pipe's bodies)
+         (1000, 24, 1, False, {"D4W_COL_PIPE3": "1", "D4W_PIPE3_CQ": "4", "D4W_PIPE3_THREADS": "32"})]    # 5 x 5 x 4, 3 chunks
 
 
 def test_fk_pipeline_emulation(tmpdir_mod):
