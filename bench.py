@@ -170,7 +170,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     steps, warmup = max(1, args.steps), max(0, args.warmup)
-    cores = os.cpu_count() or 1
+    cores = len(os.sched_getaffinity(0)) or 1
     avail = mem_available_gb()
     full = avail >= 110.0 and os.environ.get("D4W_REF_FULL", "1") != "0"
     nx = NX if full else 1000
@@ -247,6 +247,7 @@ def main():
     if args.impl == "reference":
         return run_reference(args, rank, world)
 
+    orig_affinity = os.sched_getaffinity(0)
     numa = bind_to_gpu_numa(local)
     import numpy as np
     import torch
@@ -600,7 +601,11 @@ def main():
         if sharded:
             line["sharded_fk"] = sharded
         if not args.no_cpu_baseline and world == 1:
-            cores = os.cpu_count() or 1
+            try:
+                os.sched_setaffinity(0, orig_affinity)      # the CPU baseline may use every host core again
+            except Exception:                               # noqa: BLE001
+                pass
+            cores = len(os.sched_getaffinity(0))
             cv, ct = time_cpu(1000, 1, 0, cores)
             sv, st = time_cpu(CPU_SAMPLE_NX, 1, 0, None)
             line["cpu_baseline"] = {"value": cv, "unit": "channels/s", "cores": cores, "kind": "port",

@@ -108,7 +108,7 @@ def test_bench_reference_arm_contract():
                 "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert key in line, key
     assert line["impl"] == "reference" and line["unit"] == "channels/s" and line["value"] > 0
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] == os.cpu_count() and "sample" in line["cpu_baseline"]
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0)) and "sample" in line["cpu_baseline"]
     assert line["cpu_baseline"]["single_thread"]["cores"] == 1 and line["cpu_baseline"]["single_thread"]["value"] > 0
     assert line["steps"] >= 1 and line["config"]["workload"].startswith("synthetic 10000 ch x 120000 samp")
     assert line["e2e"]["value"] == line["value"] and line["e2e"]["h2d_bytes_per_step"] == 0
