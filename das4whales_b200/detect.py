@@ -36,9 +36,28 @@ def _host1d(a):
     return np.asarray(a, dtype=np.float64).ravel()
 
 
+_MAX_TAPS = 9000        # the overlap-save correlator takes templates of up to 9 999 taps; longer ones are cut into pieces
+
+
 def _lags_on_device(x_dev, y_host):
-    """z[tau] = sum_n x[n + tau] y[n] for tau = 0 .. len(x) - 1 (float32 CUDA tensor), y = FIR taps on the host."""
-    return _rows.cross_correlogram(x_dev, [y_host], normalize=False)[0][0]
+    """z[tau] = sum_n x[n + tau] y[n] for tau = 0 .. len(x) - 1 (float32 CUDA tensor), y = FIR taps on the host.
+    Long tap vectors are split into pieces of <= 9 000 taps: the correlation with piece p (taps p*B ...) is the piece's own
+    correlogram read p*B lags later, so the pieces' shifted correlograms add up to the full one."""
+    import torch
+    y = np.asarray(y_host, dtype=np.float64).ravel()
+    nz = np.nonzero(y)[0]
+    L = int(nz[-1]) + 1 if len(nz) else 1
+    if L <= _MAX_TAPS:
+        return _rows.cross_correlogram(x_dev, [y], normalize=False)[0][0]
+    n = x_dev.shape[1]
+    out = torch.zeros(n, dtype=torch.float32, device=x_dev.device)
+    for p0 in range(0, min(L, n), _MAX_TAPS):
+        piece = y[p0:min(L, p0 + _MAX_TAPS)]
+        if not np.any(piece):
+            continue
+        z = _rows.cross_correlogram(x_dev, [piece], normalize=False)[0][0]          # lags of the piece alone
+        out[: n - p0] += z[p0:]
+    return out
 
 
 def shift_xcorr(x, y):

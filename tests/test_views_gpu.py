@@ -63,6 +63,14 @@ def test_shift_xcorr_unequal_lengths(dw, golden):
         assert rel_err(rn, g["snx_" + tag])[0] <= TOL, tag
 
 
+def test_shift_xcorr_long_dense_template(dw):
+    """equal-length dense operands far beyond the correlator's 9 999-tap limit (pieces of 9 000 taps, summed shifted)"""
+    rng = np.random.default_rng(12)
+    a, b = rng.standard_normal(25000), rng.standard_normal(25000)
+    r = dw.detect.shift_xcorr(a, b)
+    assert rel_err(r, D.shift_xcorr(a, b))[0] <= TOL
+
+
 def test_shift_xcorr_accepts_cuda_tensors(dw):
     import torch
     rng = np.random.default_rng(2)
