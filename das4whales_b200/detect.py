@@ -36,12 +36,12 @@ def _host1d(a):
     return np.asarray(a, dtype=np.float64).ravel()
 
 
-_MAX_TAPS = 9000        # the overlap-save correlator takes templates of up to 9 999 taps; longer ones are cut into pieces
+_MAX_TAPS = 2400        # one pass of the overlap-save correlator takes templates of up to 2 500 taps; longer ones are cut into pieces
 
 
 def _lags_on_device(x_dev, y_host):
     """z[tau] = sum_n x[n + tau] y[n] for tau = 0 .. len(x) - 1 (float32 CUDA tensor), y = FIR taps on the host.
-    Long tap vectors are split into pieces of <= 9 000 taps: the correlation with piece p (taps p*B ...) is the piece's own
+    Long tap vectors are split into pieces of <= 2 400 taps: the correlation with piece p (taps p*B ...) is the piece's own
     correlogram read p*B lags later, so the pieces' shifted correlograms add up to the full one."""
     import torch
     y = np.asarray(y_host, dtype=np.float64).ravel()

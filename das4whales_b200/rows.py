@@ -83,18 +83,18 @@ def row_stats(x, seglen=0):
 
 # ------------------------------------------------------------------------------ matched filter
 def _pick_block(L, ns=0):
-    """Overlap-save block length.  Lengths of the form 2^a * 25 * 25 end in odd-radix stages, which keeps the
-    8-byte shared-memory accesses of the last stages conflict-free (a power of two would end in a stride-16
-    radix-16 stage: 6x the wavefronts); 2500 keeps three CTAs per SM with 94 % of each block valid."""
-    # 2520 = 5 * 7 * 8 * 9: prime-factor blocks (no twiddles, csrc/fft_pfa.cuh) -- the default for templates up to 315 taps
-    if L <= 2520 // 8 and not (ns and (ns + (2520 - L)) // (2520 - L + 1) > 512) and _os.environ.get("D4W_XCORR_PFA", "1") != "0":
+    """Overlap-save block length for templates of L taps.  2520 = 5 * 7 * 8 * 9: prime-factor blocks (no twiddles,
+    csrc/fft_pfa.cuh), the default up to 315 taps (>= 87 % of each block valid); longer templates use Cooley-Tukey blocks of
+    2500 / 5000 samples (three float2 buffers of a block must fit one SM's shared memory, so 5000 is the largest block and
+    2500 taps the longest template one pass can take -- detect.shift_xcorr cuts longer ones into pieces)."""
+    def nseg(nb):
+        return (ns + (nb - L)) // (nb - L + 1) if ns else 0
+    if L <= 2520 // 8 and nseg(2520) <= 512 and _os.environ.get("D4W_XCORR_PFA", "1") != "0":
         return 2520
-    for nb in (1250, 2500, 5000, 10000):
-        if ns and (ns + (nb - L)) // (nb - L + 1) > 512 and nb < 10000:
-            continue                                  # row statistics keep at most 512 segment prefixes per row
-        if nb >= 8 * L or (nb == 10000 and nb >= L + 1):
+    for nb, lmax in ((1250, 156), (2500, 312), (5000, 2500)):
+        if L <= lmax and (nseg(nb) <= 512 or nb == 5000):   # row statistics keep at most 512 segment prefixes per row
             return nb
-    raise ValueError(f"template with {L} taps is too long for the overlap-save matched filter (max 9999)")
+    raise ValueError(f"template with {L} taps is too long for one pass of the overlap-save matched filter (max 2500 taps)")
 
 
 def cross_correlogram(x, templates, normalize=True):

@@ -64,7 +64,7 @@ def test_shift_xcorr_unequal_lengths(dw, golden):
 
 
 def test_shift_xcorr_long_dense_template(dw):
-    """equal-length dense operands far beyond the correlator's 9 999-tap limit (pieces of 9 000 taps, summed shifted)"""
+    """equal-length dense operands far beyond the correlator's 2 500-tap limit (pieces of 2 400 taps, summed shifted)"""
     rng = np.random.default_rng(12)
     a, b = rng.standard_normal(25000), rng.standard_normal(25000)
     r = dw.detect.shift_xcorr(a, b)
