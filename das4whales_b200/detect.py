@@ -222,7 +222,7 @@ def nxcorr2d(spectro, kernel):
     K = np.ascontiguousarray(_host2d(kernel), dtype=np.float64)
     corr = _imp.filter2D(S, None, K, border="zeros")
     s_std = float(_rows.row_stats(S.reshape(1, -1))[0][0, 2].sqrt().item())      # population std of the whole spectrogram
-    out = corr.max(dim=0).values / (s_std * float(np.std(K)) * S.shape[1])
+    out = _rows.row_max(corr.t().contiguous()) / (s_std * float(np.std(K)) * S.shape[1])      # max over the frequency lags
     return out if tens else out.to(torch.float64).cpu().numpy()
 
 
