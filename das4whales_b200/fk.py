@@ -187,6 +187,12 @@ class FkMask:
     def nnz(self):
         return int(np.count_nonzero(self.todense()))
 
+    @property
+    def data(self):
+        """Non-zero values, like sparse.COO.data (the reference's tools.disp_comprate reads `.data.nbytes`, tools.py:248)."""
+        d = self.todense()
+        return d[d != 0]
+
     def __repr__(self):
         return f"<FkMask {self.kind} shape={self.shape}>"
 

@@ -146,3 +146,11 @@ def test_dense_mask_cache_sees_in_place_changes(dw):
     m *= 0.5
     y1 = dw.dsp.fk_filter_filt(x, m)
     assert rel_err(y1, 0.5 * y0)[0] <= 1e-6
+
+
+def test_fkmask_has_the_sparse_coo_surface_the_reference_prints(dw):
+    """tools.disp_comprate (tools.py:239-257) reads mask.data.nbytes and mask.todense(); scripts call it on every hybrid mask."""
+    m = dw.dsp.hybrid_ninf_filter_design((64, 400), [0, 64, 1], 2.0419046878814697, FS, 1350., 1450., 3300, 3450, 14., 30.)
+    dense = m.todense()
+    assert m.data.ndim == 1 and m.data.size == np.count_nonzero(dense) == m.nnz
+    assert m.data.nbytes > 0 and dense.size * dense.itemsize >= m.data.nbytes
