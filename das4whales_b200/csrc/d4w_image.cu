@@ -72,6 +72,7 @@ extern "C" int d4w_mask_upsample_mul(const float* trace, int nx, int ns, const f
     if (!mask || (!out && !mask_out) || (out && !trace) || nx < 1 || ns < 1 || mh < 1 || mw < 1)
         return fail(D4W_ERR_ARG, "d4w_mask_upsample_mul: bad argument");
     if (nx > 65535) return fail(D4W_ERR_UNSUPPORTED, "d4w_mask_upsample_mul: more than 65535 rows per call");
+    if (mh > nx || mw > ns) return fail(D4W_ERR_ARG, "d4w_mask_upsample_mul: the mask must not be larger than the trace (upsampling only)");
     dim3 grid((ns + 255) / 256, nx);
     k_mask_upsample_mul<<<grid, 256, 0, (cudaStream_t)stream_v>>>(trace, nx, ns, mask, mh, mw, out, mask_out);
     D4W_CHECK_LAUNCH("k_mask_upsample_mul");

@@ -199,22 +199,28 @@ k_filter2d(const float* __restrict__ in, int h, int w, const float* __restrict__
 static __global__ void __launch_bounds__(256)
 k_mask_upsample_mul(const float* __restrict__ trace, int nx, int ns, const float* __restrict__ mask, int mh, int mw,
                     float* __restrict__ out, unsigned char* __restrict__ mask_out) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    // the rows of the small mask that contribute to output row c (blockIdx.y) with a non-zero weight are the same for the
+    // whole CTA: worked out once, then every thread only tests its <= 3 columns of those rows
+    __shared__ int s_rows[8];
+    __shared__ int s_nrows;
     const int c = blockIdx.y;
+    if (threadIdx.x == 0) {
+        const AaSpan sy = aa_span(c, mh, nx);
+        int n = 0;
+        for (int jy = 0; jy < sy.xsize && n < 8; ++jy)
+            if (aa_tri(((float)(jy + sy.xmin) - sy.center + 0.5f) * sy.invscale) != 0.f) s_rows[n++] = sy.xmin + jy;
+        s_nrows = n;
+    }
+    __syncthreads();
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= ns) return;
-    const AaSpan sy = aa_span(c, mh, nx), sx = aa_span(t, mw, ns);
-    float v = 0.f;
-    for (int jy = 0; jy < sy.xsize; ++jy) {
-        const float wy = aa_tri(((float)(jy + sy.xmin) - sy.center + 0.5f) * sy.invscale);
-        if (wy == 0.f) continue;
-        const float* r = mask + (size_t)(sy.xmin + jy) * mw + sx.xmin;
-        for (int jx = 0; jx < sx.xsize; ++jx) {
-            const float wx = aa_tri(((float)(jx + sx.xmin) - sx.center + 0.5f) * sx.invscale);
-            v += wy * wx * r[jx];
-        }
+    const AaSpan sx = aa_span(t, mw, ns);
+    bool on = false;
+    for (int jx = 0; jx < sx.xsize; ++jx) {
+        if (aa_tri(((float)(jx + sx.xmin) - sx.center + 0.5f) * sx.invscale) == 0.f) continue;
+        for (int r = 0; r < s_nrows; ++r) on = on || (mask[(size_t)s_rows[r] * mw + sx.xmin + jx] != 0.f);
     }
     const size_t o = (size_t)c * ns + t;
-    const bool on = v != 0.f;
     if (out) out[o] = on ? trace[o] : 0.f * trace[o];
     if (mask_out) mask_out[o] = on ? 1 : 0;
 }
