@@ -20,6 +20,7 @@ struct d4w_fft_plan {
     int* d_k2pos = nullptr;
     int pfa = 0;                 // n == 2520: prime-factor blocks of the matched filter (fft_pfa.cuh)
     int* d_tpos = nullptr;       // pfa: position of time index i
+    float2* d_wn = nullptr;      // exp(-2 pi i j / n), j < n (sliding-DFT STFT)
 };
 
 extern "C" int d4w_fft_plan_create(d4w_fft_plan** out, int n, int device) {
@@ -68,6 +69,11 @@ extern "C" int d4w_fft_plan_create(d4w_fft_plan** out, int n, int device) {
     cudaError_t e = upload(&p->d_tw, make_twiddles(n));
     if (e == cudaSuccess) e = upload(&p->d_k2pos, k2pos);
     if (e == cudaSuccess && p->pfa) e = upload(&p->d_tpos, tpos);
+    if (e == cudaSuccess && n <= 4096) {
+        std::vector<float2> wn((size_t)n);
+        for (int j = 0; j < n; ++j) { const double a = -2.0 * M_PI * (double)j / (double)n; wn[j] = make_float2((float)std::cos(a), (float)std::sin(a)); }
+        e = upload(&p->d_wn, wn);
+    }
     if (e != cudaSuccess) { d4w_fft_plan_destroy(p); return fail(D4W_ERR_CUDA, std::string("fft plan: ") + cudaGetErrorString(e)); }
     *out = p;
     return D4W_OK;
@@ -76,7 +82,7 @@ extern "C" int d4w_fft_plan_create(d4w_fft_plan** out, int n, int device) {
 extern "C" int d4w_fft_plan_destroy(d4w_fft_plan* p) {
     if (!p) return D4W_OK;
     DeviceGuard guard(p->device);
-    cudaFree(p->d_tw); cudaFree(p->d_k2pos); cudaFree(p->d_tpos);
+    cudaFree(p->d_tw); cudaFree(p->d_k2pos); cudaFree(p->d_tpos); cudaFree(p->d_wn);
     delete p;
     return D4W_OK;
 }
@@ -380,6 +386,47 @@ extern "C" int d4w_stft_mag(d4w_fft_plan* p, const float* x, float* out, int nx,
     k_stft_mag<<<grid, 256, smem, (cudaStream_t)stream_v>>>(sp, x, dev_window, out);
     D4W_CHECK_LAUNCH("k_stft_mag");
     return D4W_OK;
+}
+
+// sliding-DFT variant for a band of bins of heavily overlapping Hann frames (k_stft_slide); n_fft = hop * P
+template <int H, int P>
+static int launch_stft_slide(d4w_fft_plan* p, const float* x, float* out, int nx, const SlideParams& sp, cudaStream_t st) {
+    const int G = kSlideG, R = P * sp.Q;
+    const size_t smem = ((size_t)G * R * H + H * P) * sizeof(float) + (size_t)G * P * sp.nYp * sizeof(float2);
+    if (smem > p->smem_cap) return fail(D4W_ERR_UNSUPPORTED, "d4w_stft_slide: tile does not fit shared memory");
+    D4W_CUDA_TRY(cudaFuncSetAttribute(k_stft_slide<H, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_cap));
+    const int threads = (G * sp.nY + 31) / 32 * 32;
+    dim3 grid((sp.nframes + G * R - 1) / (G * R), nx);
+    k_stft_slide<H, P><<<grid, threads, smem, st>>>(sp, x, p->d_wn, out);
+    D4W_CHECK_LAUNCH("k_stft_slide");
+    return D4W_OK;
+}
+
+extern "C" int d4w_stft_slide_supported(int nfft, int hop, int nbins) {
+    if (!env_int("D4W_STFT_SLIDE", 1)) return 0;
+    if (nbins < 1 || kSlideG * (nbins + 2) > kSlideMaxThreads) return 0;
+    return (nfft == 160 && hop == 8) || (nfft == 128 && hop == 8) || (nfft == 256 && hop == 16) || (nfft == 96 && hop == 4);
+}
+
+extern "C" int d4w_stft_slide(d4w_fft_plan* p, const float* x, float* out, int nx, int ns, int hop, int bin_lo, int bin_hi,
+                              void* stream_v) {
+    if (!p || !x || !out) return fail(D4W_ERR_ARG, "d4w_stft_slide: null argument");
+    if (bin_lo < 0 || bin_hi > p->n / 2 || bin_lo > bin_hi) return fail(D4W_ERR_ARG, "d4w_stft_slide: bad bin range");
+    if (nx < 1 || ns < 1) return fail(D4W_ERR_ARG, "d4w_stft_slide: empty input");
+    if (nx > 65535) return fail(D4W_ERR_UNSUPPORTED, "d4w_stft_slide: more than 65535 rows per call");
+    const int nbins = bin_hi - bin_lo + 1;
+    if (!d4w_stft_slide_supported(p->n, hop, nbins) || !p->d_wn)
+        return fail(D4W_ERR_UNSUPPORTED, "d4w_stft_slide: (n_fft, hop, band) not covered, use d4w_stft_mag");
+    DeviceGuard guard(p->device);
+    SlideParams sp{};
+    sp.ns = ns; sp.nframes = 1 + ns / hop; sp.nbins = nbins; sp.bin_lo = bin_lo;
+    sp.nY = nbins + 2; sp.nYp = sp.nY | 1;                   // odd pitch: conflict-free 8-byte reads along frames
+    sp.Q = std::max(1, env_int("D4W_SLIDE_Q", 5));
+    cudaStream_t st = (cudaStream_t)stream_v;
+    if (p->n == 160) return launch_stft_slide<8, 20>(p, x, out, nx, sp, st);
+    if (p->n == 128) return launch_stft_slide<8, 16>(p, x, out, nx, sp, st);
+    if (p->n == 256) return launch_stft_slide<16, 16>(p, x, out, nx, sp, st);
+    return launch_stft_slide<4, 24>(p, x, out, nx, sp, st);
 }
 
 // ------------------------------------------------------------------ per-channel FFT magnitude (dsp.get_fx)

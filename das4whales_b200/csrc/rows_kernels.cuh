@@ -900,6 +900,105 @@ k_stft_mag(StftParams sp, const float* __restrict__ x, const float* __restrict__
 }
 
 
+// ------------------------------------------------------------------ sliding-DFT STFT magnitude for a band of bins
+// The spectrogram-correlation detector (detect.py:650-708) asks for ~31 of the 81 bins of 160-sample frames that overlap
+// by 95 % (hop 8): consecutive frames share 152 of 160 samples, and the FFT per frame above recomputes all of it.  With
+// n_fft = H * P (H = hop) a frame is P blocks of H samples; per bin k
+//     B_b[k]     = sum_{t<H} x[b*H + t] W^{tk}                       (block partial sum, W = exp(-2 pi i / n_fft))
+//     Y_{m+1}[k] = (Y_m[k] - B_m[k] + B_{m+P}[k]) * W^{-Hk}          (rectangular-window DFT slides by one block)
+//     S_m[k]     = Y_m[k]/2 - (Y_m[k-1] + Y_m[k+1])/4                (periodic Hann = three-bin combination)
+// so a (frame, bin) costs one 2H-FMA block sum, one complex rotation and two complex adds.  Each thread owns one bin of one
+// run of R = P*Q frames: Y is re-summed from its P blocks at the start of every run (Horner in W^{Hk}; the recursion error
+// stays ~1e-6 of max|S| even for R = 240, measured in fp32 against the fp64 oracle), the last P block sums live in
+// registers (the frame loop is unrolled P times so the ring index is static).  Every P frames the CTA's G runs drop their
+// Y values in a shared tile from which all threads form |S| and store frame-contiguous segments.
+struct SlideParams { int ns, nframes, nbins, bin_lo, nY, nYp, Q; };
+constexpr int kSlideG = 8;                      // runs per CTA
+constexpr int kSlideMaxThreads = 352;           // 8 runs x up to 44 bins
+
+template <int H>
+__device__ __forceinline__ float2 slide_block(const float* __restrict__ b, const float2 (&T)[H]) {
+    float xv[H];
+    static_for<H / 4>([&](auto qc) {
+        constexpr int q = decltype(qc)::value;
+        const float4 v = *reinterpret_cast<const float4*>(b + 4 * q);
+        xv[4 * q] = v.x; xv[4 * q + 1] = v.y; xv[4 * q + 2] = v.z; xv[4 * q + 3] = v.w;
+    });
+    float re = xv[0], im = 0.f;                 // T[0] = 1
+    static_for<H - 1>([&](auto tc) {
+        constexpr int t = decltype(tc)::value + 1;
+        re = fmaf(xv[t], T[t].x, re);
+        im = fmaf(xv[t], T[t].y, im);
+    });
+    return make_float2(re, im);
+}
+
+template <int H, int P>
+static __global__ void __launch_bounds__(kSlideMaxThreads, 2)
+k_stft_slide(SlideParams sp, const float* __restrict__ x, const float2* __restrict__ wn, float* __restrict__ out) {
+    constexpr int N = H * P, G = kSlideG;
+    extern __shared__ __align__(16) float sl_smem[];
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int R = P * sp.Q, nY = sp.nY, nYp = sp.nYp;
+    const int nxs = G * R * H + N;                                   // samples of frames [M0, M0 + G*R) plus one block
+    float* xs = sl_smem;
+    float2* Yt = reinterpret_cast<float2*>(sl_smem + nxs);          // [G][P][nYp]
+    const size_t row = blockIdx.y;
+    const int M0 = blockIdx.x * G * R;
+    const float* r = x + row * (size_t)sp.ns;
+    const long long s0 = (long long)M0 * H - N / 2;
+    for (int i = tid; i < nxs; i += nthr) {
+        const long long s = s0 + i;
+        xs[i] = (s >= 0 && s < sp.ns) ? r[s] : 0.f;
+    }
+    const int g = tid / nY, kk = tid - g * nY;
+    const bool act = g < G;
+    float2 T[H], w;
+    {
+        int k = (sp.bin_lo - 1 + kk) % N;
+        if (k < 0) k += N;                                           // bin -1 is bin N-1; no special case for the edges
+        static_for<H>([&](auto tc) { constexpr int t = decltype(tc)::value; T[t] = wn[(t * k) % N]; });
+        w = wn[(H * k) % N];
+    }
+    __syncthreads();
+    const float* xb = xs + (size_t)(act ? g : 0) * R * H;
+    float2 ring[P], Y = make_float2(0.f, 0.f);
+    static_for<P>([&](auto ic) {
+        constexpr int p = P - 1 - decltype(ic)::value;
+        ring[p] = slide_block<H>(xb + p * H, T);
+        Y = make_float2(fmaf(Y.x, w.x, fmaf(-Y.y, w.y, ring[p].x)), fmaf(Y.x, w.y, fmaf(Y.y, w.x, ring[p].y)));
+    });
+    float* orow = out + row * (size_t)sp.nbins * sp.nframes;
+    for (int q = 0; q < sp.Q; ++q) {
+        if (act) {
+            float2* yt = Yt + (size_t)(g * P) * nYp + kk;
+            const float* xq = xb + (size_t)(q * P + P) * H;          // block entering after local frame q*P + j
+            static_for<P>([&](auto jc) {
+                constexpr int j = decltype(jc)::value;
+                yt[j * nYp] = Y;
+                const float2 E = slide_block<H>(xq + j * H, T);
+                const float dx = Y.x - ring[j].x + E.x, dy = Y.y - ring[j].y + E.y;
+                Y = make_float2(fmaf(dx, w.x, dy * w.y), fmaf(dy, w.x, -dx * w.y));      // times conj(w) = W^{-Hk}
+                ring[j] = E;
+            });
+        }
+        __syncthreads();
+        const int mq = M0 + q * P;
+        for (int i = tid; i < sp.nbins * (G * P); i += nthr) {
+            const int fl = i % P, t2 = i / P;
+            const int gg = t2 % G, o = t2 / G;
+            const int m = mq + gg * R + fl;
+            if (m < sp.nframes) {
+                const float2* y = Yt + (size_t)(gg * P + fl) * nYp + o;
+                const float2 a = y[0], b = y[1], c = y[2];
+                const float re = 0.5f * b.x - 0.25f * (a.x + c.x), im = 0.5f * b.y - 0.25f * (a.y + c.y);
+                orow[(size_t)o * sp.nframes + m] = sqrtf(re * re + im * im);
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // ------------------------------------------------------------------ per-row median of non-negative floats
 // np.median over each row (detect.xcorr2d divides by median(spectro), detect.py:600).  Exact
 // 3-pass radix select on the float bit patterns (monotone for x >= 0): 11 + 11 + 10 bits, the

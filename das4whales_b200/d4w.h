@@ -162,6 +162,15 @@ int d4w_sosfiltfilt(const float* dev_x, float* dev_y, float* dev_tmp, int nx, in
 int d4w_stft_mag(d4w_fft_plan* plan, const float* dev_x, float* dev_out, int nx, int ns, int hop,
                  const float* dev_window, int bin_lo, int bin_hi, void* stream);
 
+/* Same result as d4w_stft_mag with the periodic Hann window, for a band of bins of heavily overlapping frames
+ * (n_fft = hop * P): sliding DFT, every sample enters one block sum per bin instead of one FFT per frame.  Shapes covered:
+ * d4w_stft_slide_supported(n_fft, hop, bin_hi - bin_lo + 1) != 0; anything else returns D4W_ERR_UNSUPPORTED.
+ * Replaces the librosa.stft call of detect.get_sliced_nspectrogram inside the channel loop of
+ * detect.compute_cross_correlogram_spectrocorr (/root/reference/src/das4whales/detect.py:334-408, :700-707). */
+int d4w_stft_slide_supported(int nfft, int hop, int nbins);
+int d4w_stft_slide(d4w_fft_plan* plan, const float* x, float* out, int nx, int ns, int hop, int bin_lo, int bin_hi,
+                   void* stream);
+
 /* ---- spectrogram-correlation detector: detect.xcorr2d / compute_cross_correlogram_spectrocorr
  *      (detect.py:579-602, :650-708).  Per-row median / maximum of a float32 matrix [nrows][n]
  *      (entries must be >= 0 for the median), and

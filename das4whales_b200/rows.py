@@ -280,9 +280,14 @@ def stft_mag(x, nfft, hop, bin_lo=0, bin_hi=None):
         _tab_cache[key] = torch.from_numpy(sp.get_window("hann", nfft, fftbins=True).astype(np.float32)).to(x.device)
     win = _tab_cache[key]
     L = _lib.lib()
+    slide = bool(L.d4w_stft_slide_supported(int(nfft), int(hop), bin_hi - bin_lo + 1))    # band of bins, hop | n_fft
     with torch.cuda.device(dev):
         for r0 in range(0, nx, 65535):
             r1 = min(nx, r0 + 65535)
+            if slide:
+                _lib.check(L.d4w_stft_slide(plan.ptr, _lib.ptr(x[r0:r1], "float*"), _lib.ptr(out[r0:r1], "float*"), r1 - r0, ns,
+                                            int(hop), int(bin_lo), bin_hi, _lib.stream_ptr()), "stft_slide")
+                continue
             _lib.check(L.d4w_stft_mag(plan.ptr, _lib.ptr(x[r0:r1], "float*"), _lib.ptr(out[r0:r1], "float*"), r1 - r0, ns,
                                       int(hop), _lib.ptr(win, "float*"), int(bin_lo), bin_hi, _lib.stream_ptr()), "stft_mag")
     return out
