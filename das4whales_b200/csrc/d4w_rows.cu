@@ -390,12 +390,15 @@ extern "C" int d4w_stft_mag(d4w_fft_plan* p, const float* x, float* out, int nx,
 
 // sliding-DFT variant for a band of bins of heavily overlapping Hann frames (k_stft_slide); n_fft = hop * P
 template <int H, int P>
-static int launch_stft_slide(d4w_fft_plan* p, const float* x, float* out, int nx, const SlideParams& sp, cudaStream_t st) {
-    const int G = kSlideG, R = P * sp.Q;
-    const size_t smem = ((size_t)G * R * H + H * P) * sizeof(float) + (size_t)G * P * sp.nYp * sizeof(float2);
+static int launch_stft_slide(d4w_fft_plan* p, const float* x, float* out, int nx, SlideParams sp, cudaStream_t st) {
+    const int G = kSlideG;
+    auto bytes = [&](int Q) { return ((size_t)G * P * Q * H + H * P) * sizeof(float) + (size_t)G * P * sp.nYp * sizeof(float2); };
+    while (sp.Q > 1 && bytes(sp.Q) > 110 * 1024) --sp.Q;          // two CTAs per SM (the register budget allows no more)
+    const int R = P * sp.Q;
+    const size_t smem = bytes(sp.Q);
     if (smem > p->smem_cap) return fail(D4W_ERR_UNSUPPORTED, "d4w_stft_slide: tile does not fit shared memory");
     D4W_CUDA_TRY(cudaFuncSetAttribute(k_stft_slide<H, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_cap));
-    const int threads = (G * sp.nY + 31) / 32 * 32;
+    const int threads = std::min(kSlideMaxThreads, std::max((G * sp.nY + 31) / 32 * 32, (2 * G * P + 31) / 32 * 32));
     dim3 grid((sp.nframes + G * R - 1) / (G * R), nx);
     k_stft_slide<H, P><<<grid, threads, smem, st>>>(sp, x, p->d_wn, out);
     D4W_CHECK_LAUNCH("k_stft_slide");
@@ -421,7 +424,7 @@ extern "C" int d4w_stft_slide(d4w_fft_plan* p, const float* x, float* out, int n
     SlideParams sp{};
     sp.ns = ns; sp.nframes = 1 + ns / hop; sp.nbins = nbins; sp.bin_lo = bin_lo;
     sp.nY = nbins + 2; sp.nYp = sp.nY | 1;                   // odd pitch: conflict-free 8-byte reads along frames
-    sp.Q = std::max(1, env_int("D4W_SLIDE_Q", 5));
+    sp.Q = std::max(1, env_int("D4W_SLIDE_Q", 8));
     cudaStream_t st = (cudaStream_t)stream_v;
     if (p->n == 160) return launch_stft_slide<8, 20>(p, x, out, nx, sp, st);
     if (p->n == 128) return launch_stft_slide<8, 16>(p, x, out, nx, sp, st);

@@ -916,6 +916,12 @@ struct SlideParams { int ns, nframes, nbins, bin_lo, nY, nYp, Q; };
 constexpr int kSlideG = 8;                      // runs per CTA
 constexpr int kSlideMaxThreads = 352;           // 8 runs x up to 44 bins
 
+__device__ __forceinline__ float sqrt_approx(float v) {          // MUFU.SQRT, ~1 ulp, exact zero for zero
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+
 template <int H>
 __device__ __forceinline__ float2 slide_block(const float* __restrict__ b, const float2 (&T)[H]) {
     float xv[H];
@@ -983,16 +989,23 @@ k_stft_slide(SlideParams sp, const float* __restrict__ x, const float2* __restri
             });
         }
         __syncthreads();
-        const int mq = M0 + q * P;
-        for (int i = tid; i < sp.nbins * (G * P); i += nthr) {
-            const int fl = i % P, t2 = i / P;
-            const int gg = t2 % G, o = t2 / G;
+        // |S|: each thread walks half of the band of one frame with a three-bin window (one 8-byte read per output)
+        const int mq = M0 + q * P, nh = (sp.nbins + 1) >> 1;
+        for (int it = tid; it < 2 * G * P; it += nthr) {
+            const int half = it / (G * P), pr = it - half * (G * P);             // pr = run * P + frame of the sub-step
+            const int gg = pr / P, fl = pr - gg * P;
             const int m = mq + gg * R + fl;
-            if (m < sp.nframes) {
-                const float2* y = Yt + (size_t)(gg * P + fl) * nYp + o;
-                const float2 a = y[0], b = y[1], c = y[2];
+            if (m >= sp.nframes) continue;
+            const int o0 = half * nh, o1 = min(sp.nbins, o0 + nh);
+            const float2* y = Yt + (size_t)pr * nYp + o0;
+            float* po = orow + (size_t)o0 * sp.nframes + m;
+            float2 a = y[0], b = y[1];
+#pragma unroll 4
+            for (int o = o0; o < o1; ++o) {
+                const float2 c = y[o - o0 + 2];
                 const float re = 0.5f * b.x - 0.25f * (a.x + c.x), im = 0.5f * b.y - 0.25f * (a.y + c.y);
-                orow[(size_t)o * sp.nframes + m] = sqrtf(re * re + im * im);
+                *po = sqrt_approx(fmaf(re, re, im * im));
+                po += sp.nframes; a = b; b = c;
             }
         }
         __syncthreads();
