@@ -448,7 +448,9 @@ extern "C" int d4w_row_fft_mag(d4w_fft_plan* p, const float* x, int nx, size_t l
 // ------------------------------------------------------------------ medians / maxima / spectrogram correlation
 extern "C" int d4w_row_median(const float* x, int nrows, size_t n, float* med, void* stream) {
     if (!x || !med || nrows < 1 || n < 1) return fail(D4W_ERR_ARG, "d4w_row_median: bad argument");
-    k_row_median<<<nrows, 512, 0, (cudaStream_t)stream>>>(x, n, med);
+    const size_t smem = (size_t)kMedCap * sizeof(float);
+    D4W_CUDA_TRY(cudaFuncSetAttribute(k_row_median, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_row_median<<<nrows, kMedThreads, smem, (cudaStream_t)stream>>>(x, n, med);
     D4W_CHECK_LAUNCH("k_row_median");
     return D4W_OK;
 }
@@ -464,6 +466,17 @@ extern "C" int d4w_speccorr(const float* S, int nx, int nf, int nt, const float*
                             void* stream) {
     if (!S || !K || !med || !out || nx < 1 || nf < 1 || nt < 1 || kw < 1) return fail(D4W_ERR_ARG, "d4w_speccorr: bad argument");
     if (nx > 65535) return fail(D4W_ERR_UNSUPPORTED, "d4w_speccorr: more than 65535 rows per call");
+    {
+        const int kwp = (kw + 3) & ~3;
+        const size_t smem4 = ((size_t)nf * kwp + (size_t)nf * (kScTile + kwp)) * sizeof(float);
+        if (env_int("D4W_SPECCORR4", 1) && smem4 <= 110 * 1024) {
+            D4W_CUDA_TRY(cudaFuncSetAttribute(k_speccorr4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
+            dim3 grid4((nt + kScTile - 1) / kScTile, nx);
+            k_speccorr4<<<grid4, kScThreads, smem4, (cudaStream_t)stream>>>(S, nf, nt, K, kw, kwp, med, out);
+            D4W_CHECK_LAUNCH("k_speccorr4");
+            return D4W_OK;
+        }
+    }
     const int tile = 256;
     const size_t smem = ((size_t)nf * kw + (size_t)nf * (tile + kw)) * sizeof(float);
     if (smem > 200 * 1024) return fail(D4W_ERR_UNSUPPORTED, "d4w_speccorr: kernel too large for shared memory");

@@ -1013,9 +1013,42 @@ k_stft_slide(SlideParams sp, const float* __restrict__ x, const float2* __restri
 }
 
 // ------------------------------------------------------------------ per-row median of non-negative floats
-// np.median over each row (detect.xcorr2d divides by median(spectro), detect.py:600).  Exact
-// 3-pass radix select on the float bit patterns (monotone for x >= 0): 11 + 11 + 10 bits, the
-// row is re-read from L2 each pass.  Even counts average the two middle order statistics.
+// np.median over each row (detect.xcorr2d divides by median(spectro), detect.py:600), exact.  Even counts average the
+// two middle order statistics.
+//   select_rank: 3-pass radix select on the float bit patterns (monotone for x >= 0): 11 + 11 + 10 bits.
+//   k_row_median: rows longer than the shared buffer are bracketed first -- 16 384 evenly spaced samples are sorted in
+//   shared memory, the values 176 sample ranks (2.75 sigma of the sample rank of any quantile) either side of the median's
+//   position bound it with ~99 % probability, ONE pass over the row counts what lies below the bracket and collects what
+//   lies inside (~2 % of the row) in shared memory, and the radix select runs on that.  If the bracket misses (or ties
+//   overflow the buffer) the row falls back to the radix select over global memory, so the result never depends on luck.
+constexpr int kMedThreads = 512, kMedCap = 16384, kMedDelta = 176;
+
+// bin holding `rank` in hist[nb] (nb = 1024 or 2048) by a block-wide scan; returns (bin, rank inside the bin) to all threads
+__device__ __forceinline__ void find_bin(const unsigned int* hist, int nb, unsigned long long rank, unsigned int& bin, unsigned long long& rin) {
+    __shared__ unsigned int ws[kMedThreads / 32];
+    __shared__ unsigned int s_bin;
+    __shared__ unsigned long long s_rank;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int per = nb / kMedThreads;
+    unsigned int c[4] = {0, 0, 0, 0}, tsum = 0;
+    for (int i = 0; i < per; ++i) { c[i] = hist[tid * per + i]; tsum += c[i]; }
+    unsigned int inc = tsum;
+    for (int d = 1; d < 32; d <<= 1) { const unsigned int v = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += v; }
+    if (lane == 31) ws[wid] = inc;
+    __syncthreads();
+    unsigned long long excl = inc - tsum;
+    for (int w = 0; w < wid; ++w) excl += ws[w];
+    if (tsum > 0 && rank >= excl && rank < excl + tsum) {
+        unsigned long long acc = excl;
+        int i = 0;
+        for (; i < per - 1; ++i) { if (acc + c[i] > rank) break; acc += c[i]; }
+        s_bin = (unsigned int)(tid * per + i); s_rank = rank - acc;
+    }
+    __syncthreads();
+    bin = s_bin; rin = s_rank;
+    __syncthreads();
+}
+
 __device__ __forceinline__ unsigned int select_rank(const float* __restrict__ r, size_t n, size_t rank, unsigned int* hist) {
     unsigned int prefix = 0, mask = 0;
     const int shifts[3] = {21, 10, 0};
@@ -1029,31 +1062,94 @@ __device__ __forceinline__ unsigned int select_rank(const float* __restrict__ r,
             if ((u & mask) == prefix) atomicAdd(&hist[(u >> shifts[pass]) & (nb - 1)], 1u);
         }
         __syncthreads();
-        __shared__ unsigned int s_bin;
-        __shared__ unsigned long long s_rank;
-        if (threadIdx.x == 0) {
-            unsigned long long acc = 0;
-            int b = 0;
-            for (; b < nb; ++b) { if (acc + hist[b] > rank) break; acc += hist[b]; }
-            s_bin = (unsigned int)b; s_rank = rank - acc;
-        }
-        __syncthreads();
-        prefix |= s_bin << shifts[pass];
+        unsigned int bin; unsigned long long rin;
+        find_bin(hist, nb, rank, bin, rin);
+        prefix |= bin << shifts[pass];
         mask |= (unsigned int)(nb - 1) << shifts[pass];
-        rank = (size_t)s_rank;
-        __syncthreads();
+        rank = (size_t)rin;
     }
     return prefix;
 }
 
-static __global__ void __launch_bounds__(512)
+static __global__ void __launch_bounds__(kMedThreads)
 k_row_median(const float* __restrict__ x, size_t n, float* __restrict__ med) {
+    extern __shared__ __align__(16) float mbuf[];                // kMedCap floats: samples, then the bracket's contents
     __shared__ unsigned int hist[2048];
+    __shared__ unsigned int s_cnt;
+    __shared__ unsigned long long s_below[kMedThreads / 32];
+    __shared__ float s_lohi[2];
+    const int tid = threadIdx.x, lane = tid & 31;
     const float* r = x + (size_t)blockIdx.x * n;
-    const float hi = __uint_as_float(select_rank(r, n, n / 2, hist));
-    float lo = hi;
-    if ((n & 1) == 0) lo = __uint_as_float(select_rank(r, n, n / 2 - 1, hist));
-    if (threadIdx.x == 0) med[blockIdx.x] = 0.5f * (lo + hi);
+    const size_t rk_hi = n / 2, rk_lo = (n & 1) ? n / 2 : n / 2 - 1;
+    const float* src = r;                                        // where the final select runs
+    size_t cnt = n, below = 0;
+    if (n <= (size_t)kMedCap) {
+        for (size_t i = tid; i < n; i += kMedThreads) mbuf[i] = r[i];
+        __syncthreads();
+        src = mbuf;
+    } else {
+        // sample size: 8192 keeps the sort cheap; rows beyond ~500 k entries need 16 384 for the bracket to fit the buffer
+        const int m = n <= 500000 ? 8192 : kMedCap;
+        for (int i = tid; i < m; i += kMedThreads) mbuf[i] = r[(size_t)(((unsigned long long)i * n + n / 2) / m)];
+        __syncthreads();
+        for (int k = 2; k <= m; k <<= 1)                         // bitonic sort, ascending; one compare-exchange per pair
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int pi = tid; pi < (m >> 1); pi += kMedThreads) {
+                    const int i = ((pi & ~(j - 1)) << 1) | (pi & (j - 1)), l = i | j;
+                    const float a = mbuf[i], b = mbuf[l];
+                    if (((i & k) == 0) ? (a > b) : (a < b)) { mbuf[i] = b; mbuf[l] = a; }
+                }
+                __syncthreads();
+            }
+        if (tid == 0) {
+            // 2.75 sigma of a quantile's sample rank (sigma = sqrt(m) / 2), shrunk if the bracket would not fit the buffer
+            long long delta = m == 8192 ? 124 : kMedDelta;
+            const long long fit = (long long)(0.45 * (double)kMedCap * (double)m / (double)n);
+            if (delta > fit) delta = fit > 1 ? fit : 1;
+            const long long ps = (long long)(((unsigned long long)rk_hi * m) / n);
+            s_lohi[0] = mbuf[max(0LL, ps - delta)];
+            s_lohi[1] = mbuf[min((long long)m - 1, ps + delta)];
+            s_cnt = 0;
+        }
+        __syncthreads();
+        const float lo = s_lohi[0], hi = s_lohi[1];
+        __syncthreads();                                         // everyone holds lo / hi before the buffer is reused
+        unsigned long long nb_ = 0;
+        for (size_t i0 = 0; i0 < n; i0 += 4 * kMedThreads) {
+            float v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {                        // entries are >= 0: -1 is outside every bracket
+                const size_t i = i0 + u * kMedThreads + tid;
+                v[u] = i < n ? r[i] : -1.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const bool ok = v[u] >= 0.f;
+                nb_ += (ok && v[u] < lo) ? 1u : 0u;
+                const bool in = ok && v[u] >= lo && v[u] <= hi;
+                const unsigned int bal = __ballot_sync(0xffffffffu, in);
+                if (bal) {
+                    unsigned int base = 0;
+                    if (lane == 0) base = atomicAdd(&s_cnt, (unsigned int)__popc(bal));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    const unsigned int pos = base + __popc(bal & ((1u << lane) - 1u));
+                    if (in && pos < (unsigned int)kMedCap) mbuf[pos] = v[u];
+                }
+            }
+        }
+        for (int d = 16; d > 0; d >>= 1) nb_ += __shfl_down_sync(0xffffffffu, nb_, d);
+        if (lane == 0) s_below[tid >> 5] = nb_;
+        __syncthreads();
+        for (int w = 0; w < kMedThreads / 32; ++w) below += (size_t)s_below[w];
+        cnt = s_cnt;
+        if (cnt <= (size_t)kMedCap && rk_lo >= below && rk_hi < below + cnt) src = mbuf;
+        else { below = 0; cnt = n; }                             // bracket missed or overflowed: select over the whole row
+        __syncthreads();
+    }
+    const float vhi = __uint_as_float(select_rank(src, cnt, rk_hi - below, hist));
+    float vlo = vhi;
+    if (rk_lo != rk_hi) vlo = __uint_as_float(select_rank(src, cnt, rk_lo - below, hist));
+    if (tid == 0) med[blockIdx.x] = 0.5f * (vlo + vhi);
 }
 
 // ------------------------------------------------------------------ spectrogram x kernel correlation (detect.xcorr2d)
@@ -1087,6 +1183,71 @@ k_speccorr(const float* __restrict__ S, int nf, int nt, const float* __restrict_
     }
     acc = fmaxf(acc, 0.f);
     out[row * nt + t] = acc / (med[row] * (float)kw);
+}
+
+// Register-tiled version (default): four consecutive outputs per thread, the time window slides through two float4
+// registers and the kernel row arrives as broadcast float4 -- 2 shared loads per 16 FMAs instead of 2 per FMA.
+// Shared layout: sk [nf][kwp] (kernel rows zero-padded to kwp = multiple of 4), st [nf][w], w = 4 * threads + kwp.
+constexpr int kScThreads = 128, kScTile = 4 * kScThreads;
+
+static __global__ void __launch_bounds__(kScThreads)
+k_speccorr4(const float* __restrict__ S, int nf, int nt, const float* __restrict__ K, int kw, int kwp,
+            const float* __restrict__ med, float* __restrict__ out) {
+    extern __shared__ __align__(16) float sh4[];
+    const int w = kScTile + kwp;
+    float* sk = sh4;                          // [nf][kwp]
+    float* st = sh4 + nf * kwp;               // [nf][w]
+    const int tid = threadIdx.x;
+    const size_t row = blockIdx.y;
+    const int t0 = blockIdx.x * kScTile;
+    const int c0 = kw / 2;
+    for (int i = tid; i < nf * kwp; i += kScThreads) {
+        const int f = i / kwp, j = i - f * kwp;
+        sk[i] = j < kw ? K[f * kw + j] : 0.f;
+    }
+    const float* Sr = S + row * (size_t)nf * nt;
+    const int fq = (nf + 3) >> 2;                                // frequency rows per staging group
+#pragma unroll
+    for (int gq = 0; gq < 4; ++gq) {
+        for (int f = gq * fq; f < min(nf, (gq + 1) * fq); ++f) {
+            const float* src = Sr + (size_t)f * nt;
+            float* dst = st + f * w;
+            for (int j = tid; j < w; j += kScThreads) {
+                const int t = t0 - c0 + j;
+                if (t >= 0 && t < nt) cp_async4(dst + j, src + t); else dst[j] = 0.f;
+            }
+        }
+        cp_async_commit();
+    }
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const int nq = kwp >> 2;
+#pragma unroll
+    for (int gq = 0; gq < 4; ++gq) {
+        if (gq == 0) cp_async_wait_group<3>(); else if (gq == 1) cp_async_wait_group<2>();
+        else if (gq == 2) cp_async_wait_group<1>(); else cp_async_wait_group<0>();
+        __syncthreads();
+        for (int f = gq * fq; f < min(nf, (gq + 1) * fq); ++f) {
+            const float4* a = reinterpret_cast<const float4*>(st + f * w) + tid;
+            const float4* b = reinterpret_cast<const float4*>(sk + f * kwp);
+            float4 cur = a[0];
+            for (int q = 0; q < nq; ++q) {
+                const float4 nxt = a[q + 1], k = b[q];
+                const float win[8] = {cur.x, cur.y, cur.z, cur.w, nxt.x, nxt.y, nxt.z, nxt.w};
+                const float kk[4] = {k.x, k.y, k.z, k.w};
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+                    for (int oo = 0; oo < 4; ++oo) acc[oo] = fmaf(win[jj + oo], kk[jj], acc[oo]);
+                cur = nxt;
+            }
+        }
+    }
+    const float den = med[row] * (float)kw;             // same expression as the untiled kernel: identical rounding
+#pragma unroll
+    for (int oo = 0; oo < 4; ++oo) {
+        const int t = t0 + 4 * tid + oo;
+        if (t < nt) out[row * nt + t] = fmaxf(acc[oo], 0.f) / den;
+    }
 }
 
 // per-row maximum (spectrogram normalisation max(S) of dsp.py:76 / detect.py:387)

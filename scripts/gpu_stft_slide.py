@@ -48,3 +48,33 @@ os.environ.pop("D4W_SLIDE_Q")
 kern = {'f0': 27., 'f1': 17., 'dur': 0.8, 'bdwidth': 4.}
 t = timed(lambda: dw.detect.compute_cross_correlogram_spectrocorr(xd, 200., [14., 30.], kern, 0.8, 0.95), reps=3)
 print(f"spectrocorr detector {nx} rows: {t:.2f} ms -> {t * 10:.1f} ms per 10 000 channels")
+
+# ---- median (sample-bracketed select) and register-tiled spectrogram correlation
+for name, a in [("rayleigh", np.abs(rng.standard_normal((7, 465031)) + 1j * rng.standard_normal((7, 465031)))),
+                ("even", rng.random((5, 200000))), ("ties", np.floor(rng.random((5, 300001)) * 7)),
+                ("half zeros", np.where(rng.random((4, 100001)) < 0.6, 0.0, rng.random((4, 100001)))),
+                ("const", np.full((3, 50000), 2.5)), ("short", rng.random((6, 16384))), ("short odd", rng.random((6, 999))),
+                ("just above cap", rng.random((6, 16385))), ("heavy tail", rng.standard_cauchy((4, 250000)) ** 2)]:
+    a = a.astype(np.float32)
+    got = rows.row_median(torch.from_numpy(a).cuda()).cpu().numpy()
+    ref = np.median(a, axis=1)
+    print(f"median {name:16s} n={a.shape[1]:7d}: exact={bool(np.array_equal(got, ref))}", flush=True)
+S = torch.from_numpy(np.abs(rng.standard_normal((3, 31, 15001))).astype(np.float32)).cuda()
+for kw in (19, 20, 21, 37):
+    Kk = rng.standard_normal((31, kw))
+    os.environ["D4W_SPECCORR4"] = "1"; o4 = rows.spectro_correlate(S, Kk)
+    os.environ["D4W_SPECCORR4"] = "0"; o1 = rows.spectro_correlate(S, Kk)
+    print(f"speccorr4 kw={kw}: bit-equal to untiled kernel = {bool(torch.equal(o4, o1))}")
+os.environ["D4W_SPECCORR4"] = "1"
+Sx = rows.stft_mag(xd, 160, 8, 11, 41)
+flat = Sx.reshape(nx, -1)
+t_med = timed(lambda: rows.row_median(flat))
+medv = rows.row_median(flat)
+Kk = rng.standard_normal((31, 20))
+t_sc = timed(lambda: rows.spectro_correlate(Sx, Kk, median=medv))
+os.environ["D4W_SPECCORR4"] = "0"
+t_sc1 = timed(lambda: rows.spectro_correlate(Sx, Kk, median=medv))
+os.environ["D4W_SPECCORR4"] = "1"
+print(f"row_median {nx} rows x {flat.shape[1]}: {t_med:.2f} ms; speccorr tiled {t_sc:.2f} ms, untiled {t_sc1:.2f} ms")
+t = timed(lambda: dw.detect.compute_cross_correlogram_spectrocorr(xd, 200., [14., 30.], kern, 0.8, 0.95), reps=3)
+print(f"spectrocorr detector {nx} rows: {t:.2f} ms -> {t * 10:.1f} ms per 10 000 channels")
