@@ -389,26 +389,39 @@ extern "C" int d4w_stft_mag(d4w_fft_plan* p, const float* x, float* out, int nx,
 }
 
 // sliding-DFT variant for a band of bins of heavily overlapping Hann frames (k_stft_slide); n_fft = hop * P
-template <int H, int P>
-static int launch_stft_slide(d4w_fft_plan* p, const float* x, float* out, int nx, SlideParams sp, cudaStream_t st) {
-    const int G = kSlideG;
-    auto bytes = [&](int Q) { return ((size_t)G * P * Q * H + H * P) * sizeof(float) + (size_t)G * P * sp.nYp * sizeof(float2); };
+template <int H, int P, int G>
+static int launch_stft_slide_g(d4w_fft_plan* p, const float* x, float* out, int nx, SlideParams sp, cudaStream_t st) {
+    auto bytes = [&](int Q) {
+        return (size_t)G * slide_run_stride(P * Q * H, H * P) * sizeof(float) + (size_t)G * P * sp.nYp * sizeof(float2);
+    };
     while (sp.Q > 1 && bytes(sp.Q) > 110 * 1024) --sp.Q;          // two CTAs per SM (the register budget allows no more)
     const int R = P * sp.Q;
     const size_t smem = bytes(sp.Q);
     if (smem > p->smem_cap) return fail(D4W_ERR_UNSUPPORTED, "d4w_stft_slide: tile does not fit shared memory");
-    D4W_CUDA_TRY(cudaFuncSetAttribute(k_stft_slide<H, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_cap));
-    const int threads = std::min(kSlideMaxThreads, std::max((G * sp.nY + 31) / 32 * 32, (2 * G * P + 31) / 32 * 32));
+    D4W_CUDA_TRY(cudaFuncSetAttribute(k_stft_slide<H, P, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_cap));
+    const int threads = std::min(kSlideMaxThreads, std::max((G * sp.nY + 31) / 32 * 32, 320));
     dim3 grid((sp.nframes + G * R - 1) / (G * R), nx);
-    k_stft_slide<H, P><<<grid, threads, smem, st>>>(sp, x, p->d_wn, out);
+    k_stft_slide<H, P, G><<<grid, threads, smem, st>>>(sp, x, p->d_wn, out);
     D4W_CHECK_LAUNCH("k_stft_slide");
     return D4W_OK;
 }
 
+// runs per CTA: narrow bands take more runs so that runs x (bins + 2) threads fill the CTA
+template <int H, int P>
+static int launch_stft_slide(d4w_fft_plan* p, const float* x, float* out, int nx, const SlideParams& sp, cudaStream_t st) {
+    // measured on 1000 x 120 000 (scripts/gpu_slide_tune.py): 16 runs only pay below ~10 bins (0.69 vs 0.86 ms for 7 bins);
+    // at 13 bins their larger sample buffer forces shorter runs and loses (1.15 vs 0.94 ms)
+    int G = sp.nY <= 10 ? 16 : 8;
+    const int forced = env_int("D4W_SLIDE_G", 0);                 // tuning override; must keep G * nY <= 320
+    if ((forced == 8 || forced == 16) && forced * sp.nY <= kSlideMaxThreads) G = forced;
+    if (G == 16) return launch_stft_slide_g<H, P, 16>(p, x, out, nx, sp, st);
+    return launch_stft_slide_g<H, P, 8>(p, x, out, nx, sp, st);
+}
+
 extern "C" int d4w_stft_slide_supported(int nfft, int hop, int nbins) {
     if (!env_int("D4W_STFT_SLIDE", 1)) return 0;
-    if (nbins < 1 || kSlideG * (nbins + 2) > kSlideMaxThreads) return 0;
-    return (nfft == 160 && hop == 8) || (nfft == 128 && hop == 8) || (nfft == 256 && hop == 16) || (nfft == 96 && hop == 4);
+    if (nbins < 1 || 8 * (nbins + 2) > kSlideMaxThreads) return 0;
+    return (nfft == 160 && hop == 8) || (nfft == 128 && hop == 8) || (nfft == 256 && hop == 16);
 }
 
 extern "C" int d4w_stft_slide(d4w_fft_plan* p, const float* x, float* out, int nx, int ns, int hop, int bin_lo, int bin_hi,
@@ -428,8 +441,7 @@ extern "C" int d4w_stft_slide(d4w_fft_plan* p, const float* x, float* out, int n
     cudaStream_t st = (cudaStream_t)stream_v;
     if (p->n == 160) return launch_stft_slide<8, 20>(p, x, out, nx, sp, st);
     if (p->n == 128) return launch_stft_slide<8, 16>(p, x, out, nx, sp, st);
-    if (p->n == 256) return launch_stft_slide<16, 16>(p, x, out, nx, sp, st);
-    return launch_stft_slide<4, 24>(p, x, out, nx, sp, st);
+    return launch_stft_slide<16, 16>(p, x, out, nx, sp, st);
 }
 
 // ------------------------------------------------------------------ per-channel FFT magnitude (dsp.get_fx)

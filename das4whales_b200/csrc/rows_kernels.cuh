@@ -913,8 +913,11 @@ k_stft_mag(StftParams sp, const float* __restrict__ x, const float* __restrict__
 // registers (the frame loop is unrolled P times so the ring index is static).  Every P frames the CTA's G runs drop their
 // Y values in a shared tile from which all threads form |S| and store frame-contiguous segments.
 struct SlideParams { int ns, nframes, nbins, bin_lo, nY, nYp, Q; };
-constexpr int kSlideG = 8;                      // runs per CTA
-constexpr int kSlideMaxThreads = 352;           // 8 runs x up to 44 bins
+constexpr int kSlideMaxThreads = 320;           // G runs x nY bins: 8 x <= 40, 16 x <= 20
+
+// floats between the sample regions of consecutive runs: R*H + N samples + padding so that the stride is 4 (mod 32) words
+// -- a warp that spans several runs then reads its (broadcast) 16-byte blocks from different banks
+__host__ __device__ inline int slide_run_stride(int RH, int N) { return RH + N + ((4 - (RH + N) % 32) + 32) % 32; }
 
 __device__ __forceinline__ float sqrt_approx(float v) {          // MUFU.SQRT, ~1 ulp, exact zero for zero
     float r;
@@ -939,23 +942,26 @@ __device__ __forceinline__ float2 slide_block(const float* __restrict__ b, const
     return make_float2(re, im);
 }
 
-template <int H, int P>
+template <int H, int P, int G>
 static __global__ void __launch_bounds__(kSlideMaxThreads, 2)
 k_stft_slide(SlideParams sp, const float* __restrict__ x, const float2* __restrict__ wn, float* __restrict__ out) {
-    constexpr int N = H * P, G = kSlideG;
+    constexpr int N = H * P;
     extern __shared__ __align__(16) float sl_smem[];
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int R = P * sp.Q, nY = sp.nY, nYp = sp.nYp;
-    const int nxs = G * R * H + N;                                   // samples of frames [M0, M0 + G*R) plus one block
-    float* xs = sl_smem;
-    float2* Yt = reinterpret_cast<float2*>(sl_smem + nxs);          // [G][P][nYp]
+    const int RL = R * H + N, RS = slide_run_stride(R * H, N);      // samples of one run (its R frames + one block), stride
+    float* xs = sl_smem;                                             // [G][RS]
+    float2* Yt = reinterpret_cast<float2*>(sl_smem + G * RS);        // [G][P][nYp]
     const size_t row = blockIdx.y;
     const int M0 = blockIdx.x * G * R;
     const float* r = x + row * (size_t)sp.ns;
-    const long long s0 = (long long)M0 * H - N / 2;
-    for (int i = tid; i < nxs; i += nthr) {
-        const long long s = s0 + i;
-        xs[i] = (s >= 0 && s < sp.ns) ? r[s] : 0.f;
+    for (int gg = 0; gg < G; ++gg) {
+        const long long s0 = (long long)(M0 + gg * R) * H - N / 2;
+        float* dst = xs + gg * RS;
+        for (int i = tid; i < RL; i += nthr) {
+            const long long s = s0 + i;
+            dst[i] = (s >= 0 && s < sp.ns) ? r[s] : 0.f;
+        }
     }
     const int g = tid / nY, kk = tid - g * nY;
     const bool act = g < G;
@@ -967,7 +973,7 @@ k_stft_slide(SlideParams sp, const float* __restrict__ x, const float2* __restri
         w = wn[(H * k) % N];
     }
     __syncthreads();
-    const float* xb = xs + (size_t)(act ? g : 0) * R * H;
+    const float* xb = xs + (size_t)(act ? g : 0) * RS;
     float2 ring[P], Y = make_float2(0.f, 0.f);
     static_for<P>([&](auto ic) {
         constexpr int p = P - 1 - decltype(ic)::value;
@@ -1016,12 +1022,12 @@ k_stft_slide(SlideParams sp, const float* __restrict__ x, const float2* __restri
 // np.median over each row (detect.xcorr2d divides by median(spectro), detect.py:600), exact.  Even counts average the
 // two middle order statistics.
 //   select_rank: 3-pass radix select on the float bit patterns (monotone for x >= 0): 11 + 11 + 10 bits.
-//   k_row_median: rows longer than the shared buffer are bracketed first -- 16 384 evenly spaced samples are sorted in
-//   shared memory, the values 176 sample ranks (2.75 sigma of the sample rank of any quantile) either side of the median's
-//   position bound it with ~99 % probability, ONE pass over the row counts what lies below the bracket and collects what
+//   k_row_median: rows longer than the shared buffer are bracketed first -- m = 2048 .. 16 384 evenly spaced samples are
+//   sorted in shared memory, the values 1.375 sqrt(m) sample ranks (2.75 sigma of a quantile's sample rank) either side of
+//   the median's position bound it with ~99 % probability, ONE pass over the row counts what lies below the bracket and collects what
 //   lies inside (~2 % of the row) in shared memory, and the radix select runs on that.  If the bracket misses (or ties
 //   overflow the buffer) the row falls back to the radix select over global memory, so the result never depends on luck.
-constexpr int kMedThreads = 512, kMedCap = 16384, kMedDelta = 176;
+constexpr int kMedThreads = 512, kMedCap = 16384;
 
 // bin holding `rank` in hist[nb] (nb = 1024 or 2048) by a block-wide scan; returns (bin, rank inside the bin) to all threads
 __device__ __forceinline__ void find_bin(const unsigned int* hist, int nb, unsigned long long rank, unsigned int& bin, unsigned long long& rin) {
@@ -1088,8 +1094,10 @@ k_row_median(const float* __restrict__ x, size_t n, float* __restrict__ med) {
         __syncthreads();
         src = mbuf;
     } else {
-        // sample size: 8192 keeps the sort cheap; rows beyond ~500 k entries need 16 384 for the bracket to fit the buffer
-        const int m = n <= 500000 ? 8192 : kMedCap;
+        // smallest sample (the sort is the expensive part) whose +-2.75 sigma bracket, ~2.75 n / sqrt(m) entries, fits 90 % of
+        // the buffer: n <= 0.9 * 16384 * sqrt(m) / 2.75
+        int m = 2048;
+        while (m < kMedCap && (double)n > 5362.0 * sqrt((double)m)) m <<= 1;
         for (int i = tid; i < m; i += kMedThreads) mbuf[i] = r[(size_t)(((unsigned long long)i * n + n / 2) / m)];
         __syncthreads();
         for (int k = 2; k <= m; k <<= 1)                         // bitonic sort, ascending; one compare-exchange per pair
@@ -1103,7 +1111,7 @@ k_row_median(const float* __restrict__ x, size_t n, float* __restrict__ med) {
             }
         if (tid == 0) {
             // 2.75 sigma of a quantile's sample rank (sigma = sqrt(m) / 2), shrunk if the bracket would not fit the buffer
-            long long delta = m == 8192 ? 124 : kMedDelta;
+            long long delta = (long long)(1.375 * sqrt((double)m));
             const long long fit = (long long)(0.45 * (double)kMedCap * (double)m / (double)n);
             if (delta > fit) delta = fit > 1 ? fit : 1;
             const long long ps = (long long)(((unsigned long long)rk_hi * m) / n);
@@ -1209,18 +1217,29 @@ k_speccorr4(const float* __restrict__ S, int nf, int nt, const float* __restrict
     const int fq = (nf + 3) >> 2;                                // frequency rows per staging group
 #pragma unroll
     for (int gq = 0; gq < 4; ++gq) {
-        for (int f = gq * fq; f < min(nf, (gq + 1) * fq); ++f) {
-            const float* src = Sr + (size_t)f * nt;
-            float* dst = st + f * w;
-            for (int j = tid; j < w; j += kScThreads) {
-                const int t = t0 - c0 + j;
-                if (t >= 0 && t < nt) cp_async4(dst + j, src + t); else dst[j] = 0.f;
+        const int f0 = gq * fq, f1 = min(nf, f0 + fq);
+        for (int j = tid; j < w; j += kScThreads) {              // column first: bounds and addresses once per column
+            const int t = t0 - c0 + j;
+            float* dst = st + f0 * w + j;
+            if (t >= 0 && t < nt) {
+                const float* src = Sr + (size_t)f0 * nt + t;
+                for (int f = f0; f < f1; ++f, dst += w, src += nt) cp_async4(dst, src);
+            } else {
+                for (int f = f0; f < f1; ++f, dst += w) *dst = 0.f;
             }
         }
         cp_async_commit();
     }
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     const int nq = kwp >> 2;
+    auto mac16 = [&](const float4& lo, const float4& hi, const float4& k) {
+        const float win[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+        const float kk[4] = {k.x, k.y, k.z, k.w};
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+            for (int oo = 0; oo < 4; ++oo) acc[oo] = fmaf(win[jj + oo], kk[jj], acc[oo]);
+    };
 #pragma unroll
     for (int gq = 0; gq < 4; ++gq) {
         if (gq == 0) cp_async_wait_group<3>(); else if (gq == 1) cp_async_wait_group<2>();
@@ -1229,17 +1248,13 @@ k_speccorr4(const float* __restrict__ S, int nf, int nt, const float* __restrict
         for (int f = gq * fq; f < min(nf, (gq + 1) * fq); ++f) {
             const float4* a = reinterpret_cast<const float4*>(st + f * w) + tid;
             const float4* b = reinterpret_cast<const float4*>(sk + f * kwp);
-            float4 cur = a[0];
-            for (int q = 0; q < nq; ++q) {
-                const float4 nxt = a[q + 1], k = b[q];
-                const float win[8] = {cur.x, cur.y, cur.z, cur.w, nxt.x, nxt.y, nxt.z, nxt.w};
-                const float kk[4] = {k.x, k.y, k.z, k.w};
-#pragma unroll
-                for (int jj = 0; jj < 4; ++jj)
-#pragma unroll
-                    for (int oo = 0; oo < 4; ++oo) acc[oo] = fmaf(win[jj + oo], kk[jj], acc[oo]);
-                cur = nxt;
+            float4 c0v = a[0], c1v;
+            int q = 0;
+            for (; q + 1 < nq; q += 2) {                         // the window ping-pongs between two registers: no moves
+                c1v = a[q + 1]; mac16(c0v, c1v, b[q]);
+                c0v = a[q + 2]; mac16(c1v, c0v, b[q + 1]);
             }
+            if (q < nq) { c1v = a[q + 1]; mac16(c0v, c1v, b[q]); }
         }
     }
     const float den = med[row] * (float)kw;             // same expression as the untiled kernel: identical rounding

@@ -16,7 +16,7 @@ def timed(fn, reps=5):
 
 rng = np.random.default_rng(5)
 for (nfft, hop, b0, b1, ns) in [(160, 8, 2, 32, 9000), (160, 8, 0, 30, 9001), (160, 8, 50, 80, 12345), (128, 8, 5, 40, 6000),
-                                (256, 16, 10, 50, 7000), (96, 4, 1, 20, 3000), (160, 8, 11, 24, 120000)]:
+                                (256, 16, 10, 50, 7000), (256, 16, 20, 27, 5000), (128, 8, 3, 18, 4000), (160, 8, 12, 24, 120000), (160, 8, 30, 30, 2000)]:
     x = rng.standard_normal((5, ns)).astype(np.float32)
     x[1] += 50 * np.sin(2 * np.pi * 0.7 * np.arange(ns) / 200).astype(np.float32)
     xd = torch.from_numpy(x).cuda()

@@ -33,11 +33,11 @@ def main():
         for w in WANT:
             if w in idx:
                 lines.append(f"  {w:72s} {r[idx[w]]:>20s} {units[idx[w]]}")
-        rd, wr, t = float(r[idx["dram__bytes_read.sum"]]), float(r[idx["dram__bytes_write.sum"]]), float(r[idx["gpu__time_duration.sum"]])
-        u = units[idx["dram__bytes_read.sum"]]
-        scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}.get(u, 1)
-        tu = {"ms": 1e-3, "us": 1e-6, "s": 1, "ns": 1e-9}.get(units[idx["gpu__time_duration.sum"]], 1e-3)
-        lines.append(f"  -> DRAM traffic {(rd + wr) * scale / 1e9:.3f} GB in {t * tu * 1e3:.3f} ms = {(rd + wr) * scale / (t * tu) / 1e9:.0f} GB/s (under the profiler)")
+        byte_scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}
+        rd = float(r[idx["dram__bytes_read.sum"]]) * byte_scale.get(units[idx["dram__bytes_read.sum"]], 1)
+        wr = float(r[idx["dram__bytes_write.sum"]]) * byte_scale.get(units[idx["dram__bytes_write.sum"]], 1)   # own unit per column
+        t = float(r[idx["gpu__time_duration.sum"]]) * {"ms": 1e-3, "us": 1e-6, "s": 1, "ns": 1e-9}.get(units[idx["gpu__time_duration.sum"]], 1e-3)
+        lines.append(f"  -> DRAM traffic {(rd + wr) / 1e9:.3f} GB in {t * 1e3:.3f} ms = {(rd + wr) / t / 1e9:.0f} GB/s (under the profiler)")
         top = sorted(((float(r[idx[k]]), k) for k in stall), reverse=True)[:6]
         lines.append("  warps stalled per issue: " + ", ".join(f"{k.split('stalled_')[1].replace('_per_issue_active.ratio', '')} {v:.2f}" for v, k in top))
         lines.append("")

@@ -171,6 +171,64 @@ def test_row_median_exact(dw):
         assert np.array_equal(med, np.median(a, axis=1).astype(np.float32)), n
 
 
+@pytest.mark.parametrize("n", [16385, 200000, 300001, 465031, 700001])
+def test_row_median_bracketed_select(dw, n):
+    """Rows longer than the shared buffer: sample bracket + one collection pass (k_row_median), incl. the cases that must
+    fall back to the radix select over the whole row (ties overflowing the bracket, constant rows)."""
+    import torch
+    from das4whales_b200 import rows
+    rng = np.random.default_rng(n)
+    a = np.stack([
+        np.abs(rng.standard_normal(n) + 1j * rng.standard_normal(n)),      # Rayleigh, like |STFT| of noise
+        rng.standard_cauchy(n) ** 2,                                       # heavy tail
+        np.floor(rng.random(n) * 5),                                       # five distinct values: the bracket overflows
+        np.where(rng.random(n) < 0.6, 0.0, rng.random(n)),                 # median inside a block of zeros
+        np.full(n, 2.5),
+        np.sort(rng.random(n)),                                            # monotone: systematic sample = exact quantiles
+    ]).astype(np.float32)
+    med = rows.row_median(torch.from_numpy(a).cuda()).cpu().numpy()
+    assert np.array_equal(med, np.median(a, axis=1).astype(np.float32))
+
+
+@pytest.mark.parametrize("nfft,hop,b0,b1,ns", [(160, 8, 2, 32, 9000), (160, 8, 0, 30, 9001), (160, 8, 50, 80, 12345),
+                                               (160, 8, 12, 24, 120000), (160, 8, 30, 30, 2000), (160, 8, 14, 20, 7),
+                                               (128, 8, 3, 18, 4000), (128, 8, 27, 64, 6001), (256, 16, 20, 27, 5000)])
+def test_stft_sliding_dft_band(dw, nfft, hop, b0, b1, ns):
+    """d4w_stft_slide (sliding DFT over a band of bins) vs the fp64 restatement of librosa.stft and vs the per-frame FFT
+    kernel; row 1 carries a strong out-of-band tone (the rectangular-window recursion sees its leakage, the Hann
+    combination has to cancel it)."""
+    import os
+    import torch
+    from das4whales_b200 import rows, _lib
+    assert _lib.lib().d4w_stft_slide_supported(nfft, hop, b1 - b0 + 1) == 1
+    rng = np.random.default_rng(ns)
+    x = rng.standard_normal((4, ns)).astype(np.float32)
+    x[1] += (50 * np.sin(2 * np.pi * 0.7 * np.arange(ns) / FS)).astype(np.float32)
+    x[2] += 1000.0                                                          # DC offset
+    xd = torch.from_numpy(x).cuda()
+    got = rows.stft_mag(xd, nfft, hop, b0, b1).cpu().numpy()
+    os.environ["D4W_STFT_SLIDE"] = "0"
+    try:
+        fft_path = rows.stft_mag(xd, nfft, hop, b0, b1).cpu().numpy()
+    finally:
+        del os.environ["D4W_STFT_SLIDE"]
+    assert got.shape == fft_path.shape == (4, b1 - b0 + 1, 1 + ns // hop)
+    for i in range(4):
+        full = np.abs(O.stft_librosa(x[i].astype(np.float64), nfft, hop))
+        ref = full[b0:b1 + 1]
+        scale = max(ref.max(), 1e-30) if i != 2 else full.max()           # the DC row is judged against its full spectrum
+        assert np.abs(got[i] - ref).max() / scale <= 2e-5, (i, np.abs(got[i] - ref).max() / scale)
+        assert np.abs(fft_path[i] - ref).max() / scale <= 2e-5
+
+
+def test_stft_sliding_dft_not_used_outside_its_shapes(dw):
+    from das4whales_b200 import _lib
+    L = _lib.lib()
+    assert L.d4w_stft_slide_supported(160, 8, 81) == 0        # whole spectrum: the per-frame FFT is cheaper
+    assert L.d4w_stft_slide_supported(160, 40, 13) == 0       # 75 % overlap
+    assert L.d4w_stft_slide_supported(100, 5, 13) == 0
+
+
 def test_sosfiltfilt_chunked_equals_sequential(dw):
     """Time-chunked recursion (warm-up from the slowest pole) vs the plain sequential kernel."""
     import os
