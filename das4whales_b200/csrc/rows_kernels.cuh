@@ -1215,7 +1215,7 @@ k_speccorr4(const float* __restrict__ S, int nf, int nt, const float* __restrict
     }
     const float* Sr = S + row * (size_t)nf * nt;
     const int fq = (nf + 3) >> 2;                                // frequency rows per staging group
-#pragma unroll
+#pragma unroll 1
     for (int gq = 0; gq < 4; ++gq) {
         const int f0 = gq * fq, f1 = min(nf, f0 + fq);
         for (int j = tid; j < w; j += kScThreads) {              // column first: bounds and addresses once per column
@@ -1223,8 +1223,10 @@ k_speccorr4(const float* __restrict__ S, int nf, int nt, const float* __restrict
             float* dst = st + f0 * w + j;
             if (t >= 0 && t < nt) {
                 const float* src = Sr + (size_t)f0 * nt + t;
+#pragma unroll 4
                 for (int f = f0; f < f1; ++f, dst += w, src += nt) cp_async4(dst, src);
             } else {
+#pragma unroll 1
                 for (int f = f0; f < f1; ++f, dst += w) *dst = 0.f;
             }
         }
@@ -1240,16 +1242,18 @@ k_speccorr4(const float* __restrict__ S, int nf, int nt, const float* __restrict
 #pragma unroll
             for (int oo = 0; oo < 4; ++oo) acc[oo] = fmaf(win[jj + oo], kk[jj], acc[oo]);
     };
-#pragma unroll
+#pragma unroll 1                                             // one copy of the FMA block: unrolled four times it missed the i-cache
     for (int gq = 0; gq < 4; ++gq) {
         if (gq == 0) cp_async_wait_group<3>(); else if (gq == 1) cp_async_wait_group<2>();
         else if (gq == 2) cp_async_wait_group<1>(); else cp_async_wait_group<0>();
         __syncthreads();
+#pragma unroll 1
         for (int f = gq * fq; f < min(nf, (gq + 1) * fq); ++f) {
             const float4* a = reinterpret_cast<const float4*>(st + f * w) + tid;
             const float4* b = reinterpret_cast<const float4*>(sk + f * kwp);
             float4 c0v = a[0], c1v;
             int q = 0;
+#pragma unroll 1
             for (; q + 1 < nq; q += 2) {                         // the window ping-pongs between two registers: no moves
                 c1v = a[q + 1]; mac16(c0v, c1v, b[q]);
                 c0v = a[q + 2]; mac16(c1v, c0v, b[q + 1]);
