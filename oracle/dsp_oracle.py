@@ -270,6 +270,36 @@ def stft_librosa(y, n_fft, hop_length):
     return np.fft.rfft(frames, axis=1).T
 
 
+def stft_sliding_band(y, n_fft, hop, bin_lo, bin_hi, run=160, dtype=np.float32):
+    """The algorithm of the CUDA kernel k_stft_slide restated with NumPy in the kernel's precision (test infrastructure: it
+    pins the numerics of the recursion on the CPU; the kernel itself is checked against stft_librosa on the GPU).
+    |librosa.stft| for bins bin_lo..bin_hi when n_fft = hop * P:  block sums B_b[k] = sum_t x[b*hop + t] W^{tk},
+    Y_{m+1} = (Y_m - B_m + B_{m+P}) W^{-hop k}, re-anchored every `run` frames (Horner over the P blocks),
+    S[k] = Y[k]/2 - (Y[k-1] + Y[k+1])/4 for the periodic Hann window."""
+    assert n_fft % hop == 0
+    P = n_fft // hop
+    cdt = np.complex64 if dtype == np.float32 else np.complex128
+    y = np.asarray(y, dtype=dtype)
+    nfr = 1 + len(y) // hop
+    ypad = np.concatenate((np.zeros(n_fft // 2, dtype), y, np.zeros(n_fft + (run + P) * hop, dtype)))
+    ks = np.arange(bin_lo - 1, bin_hi + 2)
+    T = np.exp(-2j * np.pi * np.outer(ks, np.arange(hop)) / n_fft).astype(cdt)        # W^{tk}
+    w = np.exp(-2j * np.pi * hop * ks / n_fft).astype(cdt)                             # W^{hop k}
+    nblk = len(ypad) // hop
+    B = (ypad[:nblk * hop].reshape(nblk, 1, hop).astype(cdt) * T[None]).sum(-1).astype(cdt)
+    Y = np.zeros((nfr + run, len(ks)), cdt)
+    for m0 in range(0, nfr, run):
+        acc = np.zeros(len(ks), cdt)
+        for p in range(P - 1, -1, -1):
+            acc = (acc * w + B[m0 + p]).astype(cdt)
+        for f in range(run):
+            Y[m0 + f] = acc
+            acc = ((acc - B[m0 + f] + B[m0 + f + P]) * np.conj(w)).astype(cdt)
+    Y = Y[:nfr]
+    S = dtype(0.5) * Y[:, 1:-1] - dtype(0.25) * (Y[:, :-2] + Y[:, 2:])
+    return np.abs(S).T
+
+
 def get_spectrogram(waveform, fs, nfft=128, overlap_pct=0.8):
     """|STFT| in dB re max, with linspace axes -- dsp.py:41-78."""
     hop = int(np.floor(nfft * (1 - overlap_pct)))

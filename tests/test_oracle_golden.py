@@ -108,6 +108,24 @@ def test_stft_restatement_against_scipy():
         assert rel_err(np.abs(s[:, :n]), np.abs(z[:, :n]))[0] <= 1e-10
 
 
+@pytest.mark.parametrize("n_fft,hop,b0,b1", [(160, 8, 12, 24), (160, 8, 0, 30), (160, 8, 50, 80), (128, 8, 3, 18)])
+def test_sliding_dft_recursion_numerics(n_fft, hop, b0, b1):
+    """The recursion behind d4w_stft_slide, restated in fp32 NumPy, against the fp64 STFT restatement: re-anchoring every
+    160 frames keeps it at ~1e-6 of the spectrum's maximum, also when the band only sees the leakage of a strong
+    out-of-band tone or of a DC offset (the rectangular-window values are large there, the Hann combination cancels them)."""
+    rng = np.random.default_rng(n_fft + b0)
+    ns = 20000
+    t = np.arange(ns) / 200.0
+    for y in (rng.standard_normal(ns), rng.standard_normal(ns) + 100 * np.sin(2 * np.pi * 0.7 * t), rng.standard_normal(ns) + 1e3):
+        full = np.abs(O.stft_librosa(y, n_fft, hop))
+        got = O.stft_sliding_band(y, n_fft, hop, b0, b1)
+        assert got.shape == (b1 - b0 + 1, 1 + ns // hop)
+        assert np.abs(got - full[b0:b1 + 1]).max() / full.max() <= 5e-6
+    y = rng.standard_normal(3000)                                                                     # the identity itself, in fp64
+    ref = np.abs(O.stft_librosa(y, n_fft, hop))
+    assert np.abs(O.stft_sliding_band(y, n_fft, hop, b0, b1, dtype=np.float64) - ref[b0:b1 + 1]).max() / ref.max() <= 1e-12
+
+
 @pytest.mark.skipif(not ref_loader.available(), reason="/root/reference not present (GPU box)")
 def test_oracle_against_live_reference():
     dsp, detect = ref_loader.load()
