@@ -215,6 +215,9 @@ def _taper_edges_inplace(trace):
     win = sp.windows.tukey(nt, alpha=0.03)
     width = int(np.floor(0.03 * (nt - 1) / 2.0)) + 1
     width = min(width, nt)
+    if _is_tensor(trace):
+        import torch
+        win = torch.from_numpy(win).to(trace.device, trace.dtype)
     trace[:, :width] *= win[np.newaxis, :width]
     if nt - width >= width:
         trace[:, nt - width:] *= win[np.newaxis, nt - width:]
@@ -234,7 +237,7 @@ def fk_filter_filt(trace, fk_filter_matrix, tapering=False):
         flt = _fk.FkFilter(fk_filter_matrix, shape=tuple(x.shape), device=x.device.index)
         y = flt(x, tapering=tapering)
         if tapering:
-            taper_data(trace)
+            _taper_edges_inplace(trace)          # the reference's side effect; the window is exactly 1 between the edges
         return y
     arr = np.asarray(trace)
     x = _to_device(arr)

@@ -86,6 +86,14 @@ def test_butterworth_and_taper_kat(golden):
     dw.dsp._taper_edges_inplace(y)
     import scipy.signal as sp
     assert np.array_equal(y, x * sp.windows.tukey(400, alpha=0.03)[None, :])
+    # tensor inputs of fk_filter_filt(tapering=True) get the same side effect from the edge samples only
+    import torch
+    for nt in (5, 8, 1201):
+        a = np.random.default_rng(nt).standard_normal((3, nt)).astype(np.float32)
+        t = torch.from_numpy(a.copy())
+        dw.dsp._taper_edges_inplace(t)
+        full = torch.from_numpy(a.copy()) * torch.from_numpy(sp.windows.tukey(nt, alpha=0.03)).to(torch.float32)[None, :]
+        assert torch.equal(t, full)
 
 
 def test_gabor_kernel_design_is_the_opencv_kernel(golden):
